@@ -1,0 +1,142 @@
+/*
+ * pesto_b200 -- C ABI of the B200-native (sm_100a) PeSTo forward path.
+ *
+ * Every entry point replaces one piece of the reference's Python hot path (citations are
+ * file:line into LBM-EPFL/PeSTo).  The reference has no FFI of its own (it is pure
+ * PyTorch), so this header *is* the binding surface a maintainer would add: plain
+ * pointers and sizes, no torch types.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - all `const float*`, `int64_t*` ... arguments are DEVICE pointers on the current CUDA device unless
+ *     the name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); every call only
+ *     enqueues work on that stream and never synchronises, allocates or frees device memory
+ *     (except pesto_model_finalize / pesto_model_destroy, which own the packed weights);
+ *   - return value 0 = success; otherwise a negative PESTO_E* code, with a message available
+ *     from pesto_last_error() (thread-local).  Nothing aborts the process: callers wrap
+ *     per-structure work in try/except and continue (interfaceome/apply_model.py:81-82).
+ */
+#ifndef PESTO_B200_H
+#define PESTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PESTO_OK            0
+#define PESTO_EINVAL       -1   /* bad argument (shape, null pointer, unsupported size) */
+#define PESTO_ECUDA        -2   /* a CUDA runtime call / kernel launch failed            */
+#define PESTO_ESTATE       -3   /* model not finalized, missing tensor, ...              */
+
+#define PESTO_NS           32   /* state width Ns            (model/config.py: 'Ns': 32) */
+#define PESTO_NH            2   /* attention heads Nh                                    */
+#define PESTO_NK            3   /* key width Nk                                          */
+#define PESTO_MAX_NN       64   /* neighbours kept per atom  (extract_topology(X, 64))    */
+#define PESTO_STATE_STRIDE 128  /* floats per atom record: q[32] | p_x[32] | p_y[32] | p_z[32] */
+#define PESTO_NUM_OUT       5   /* logits per residue        (model/config.py 'dm' N2)    */
+
+/* arithmetic modes of the per-edge MLPs (state, softmax and accumulators are always fp32) */
+#define PESTO_MODE_FP32     0   /* FFMA everywhere: parity mode                                     */
+#define PESTO_MODE_BF16X3   1   /* tcgen05 tensor cores, 3-term split bf16 (hi*hi + lo*hi + hi*lo)  */
+#define PESTO_MODE_BF16     2   /* tcgen05 tensor cores, single bf16 pass: speed mode, ~1e-1 logits */
+
+typedef struct pesto_model pesto_model_t;
+
+int         pesto_abi_version(void);
+const char *pesto_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Topology.  Replaces extract_topology(X, num_nn)            src/data_encoding.py:87-102
+ * and, with base = 1, also the index shift / sink padding of
+ * collate_batch_features                                       src/dataset.py:100-109.
+ *
+ * X[n_atoms,3] holds `n_seg` independent structures back to back; seg_off[n_seg+1] (int32,
+ * device) are their atom offsets.  For every atom the k nearest atoms OF ITS OWN structure are
+ * selected by (masked distance, index) ascending, where the distance is bit-exact with the
+ * reference's fp32 recipe sqrt(fma(dz,dz,fma(dy,dy,dx*dx))) and entries closer than 1e-2 get
+ * + max(D of the structure) (src/data_encoding.py:93).
+ *   base = 0: ids are 0-based inside the structure (what extract_topology returns);
+ *             columns >= structure size are filled with -1 (callers slice [:, :min(k, n)]).
+ *   base = 1: ids are 1-based global row numbers with 0 = sink in unfilled columns
+ *             (what collate_batch_features hands to Model.forward).
+ * d_out[n_atoms,k] / r_out[n_atoms,k,3] (optional, may be NULL) receive D_topk / R_topk.
+ * scratch: at least pesto_knn_scratch_bytes(n_atoms, n_seg) bytes.
+ * ------------------------------------------------------------------------------------------- */
+size_t pesto_knn_scratch_bytes(int n_atoms, int n_seg);
+int    pesto_knn(const float *X, int n_atoms, const int32_t *seg_off, int n_seg, int k, int base,
+                 int64_t *ids_out, float *d_out, float *r_out, void *scratch, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weights.  Replaces Model(config_model) + load_state_dict(torch.load(model_ckpt.pt))
+ *                                                    model/model.py:7-30, apply_model.ipynb:84-93
+ * Tensors are handed over one by one under their reference state-dict key
+ * ("em.0.weight", "sum.7.su.evm.2.bias", "spl.zdm_vec.0.weight", ...), fp32, row-major HOST
+ * memory, shapes as in the checkpoint.  pesto_model_finalize packs them into
+ * the device layout the kernels read; the model is immutable afterwards.
+ * ------------------------------------------------------------------------------------------- */
+pesto_model_t *pesto_model_create(int n_layers, const int32_t *nn_per_layer_host, int q0_dim);
+int            pesto_model_set_tensor(pesto_model_t *m, const char *key, const float *data_host, int64_t numel);
+int            pesto_model_finalize(pesto_model_t *m);
+void           pesto_model_destroy(pesto_model_t *m);
+int            pesto_model_num_layers(const pesto_model_t *m);
+int            pesto_model_layer_nn(const pesto_model_t *m, int layer);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward, stage by stage (used by the per-layer parity tests and by pesto_forward).
+ *
+ * Device layouts (DESIGN.md "Data layout in HBM"):
+ *   state  float[n_atoms+1][128]   row 0 = sink (all zero), row i+1 = atom i: q | p_x | p_y | p_z
+ *   ids32  int32[n_atoms][64]      1-based rows into `state`, 0 = sink
+ *   geom   float4[n_atoms][64]     (r_x, r_y, r_z, d) of the edge
+ * ------------------------------------------------------------------------------------------- */
+
+/* q = em(q0); p = 0; D_nn, R_nn from X and ids  --  model/model.py:34-40, src/model_operations.py:6-22.
+ * ids1[n_atoms, ids_cols] int64, 1-based, 0 = sink (geometry of sink slots uses X[-1], as the reference).
+ * scratch8: 8 bytes of device scratch ([0] bits of the global max of D_nn, [1] set non-zero if an id is out of
+ * range). */
+int pesto_prologue(const pesto_model_t *m, const float *X, const int64_t *ids1, int ids_cols,
+                   const float *q0, int n_atoms, float *state, int32_t *ids32, float *geom,
+                   void *scratch8, void *stream);
+
+/* one StateUpdateLayer -- src/model_operations.py:225-242 (gathers, StateUpdate.forward :87-154, sink reset).
+ * node_scratch: pesto_node_scratch_bytes(n_atoms) bytes.  state_in and state_out must not alias. */
+size_t pesto_node_scratch_bytes(int n_atoms);
+int    pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32,
+                          const float *geom, const float *state_in, float *state_out,
+                          void *node_scratch, int mode, void *stream);
+
+/* dense one-hot membership M[n_atoms, n_res] (fp32, the reference's 4th forward argument) -> residue
+ * column per atom.  flags[0] is set non-zero on device if some row is not one-hot. */
+int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream);
+
+/* StatePoolLayer + decoder -- src/model_operations.py:197-213, model/model.py:46-50.
+ * rid[n_atoms] residue column per atom (any order); z[n_res,5].
+ * scratch: pesto_pool_scratch_bytes(n_atoms, n_res) bytes. */
+size_t pesto_pool_scratch_bytes(int n_atoms, int n_res);
+int    pesto_pool_decode(const pesto_model_t *m, const float *state, const int32_t *rid, int n_atoms,
+                         int n_res, float *z, void *scratch, void *stream);
+
+/* copy a packed state into the reference's tensors q[n_atoms+1,32], p[n_atoms+1,3,32] (test taps) */
+int pesto_unpack_state(const float *state, int n_atoms, float *q, float *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole forward.  Replaces Model.forward(X, ids_topk, q0, M)                model/model.py:32-52
+ * Exactly one of M (dense fp32 [n_atoms, n_res]) and rid (int32 [n_atoms]) must be non-NULL.
+ * workspace: pesto_forward_workspace_bytes(n_atoms, n_res) bytes of device memory.
+ * ------------------------------------------------------------------------------------------- */
+size_t pesto_forward_workspace_bytes(int n_atoms, int n_res);
+int    pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, int ids_cols,
+                     const float *q0, const float *M, const int32_t *rid, int n_atoms, int n_res,
+                     float *z, void *workspace, size_t workspace_bytes, int mode, void *stream);
+
+/* number of kernels one pesto_forward / pesto_knn call launches (for bench.py's gpu_launches) */
+int pesto_forward_launch_count(const pesto_model_t *m, int dense_m);
+int pesto_knn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PESTO_B200_H */

@@ -1,0 +1,72 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long CPU oracle runs, opt in with PESTO_SLOW=1")
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("PESTO_SLOW") == "1":
+        return
+    skip = pytest.mark.skip(reason="slow oracle run; set PESTO_SLOW=1")
+    for item in items:
+        if "slow" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_case(name):
+    return dict(np.load(os.path.join(GOLDEN, f"case_{name}.npz")))
+
+
+def load_weights(tag):
+    return dict(np.load(os.path.join(GOLDEN, f"weights_{tag}.npz")))
+
+
+def load_config(tag):
+    with open(os.path.join(GOLDEN, f"config_{tag}.json")) as fh:
+        return json.load(fh)
+
+
+def case_tensors(c):
+    """(X, el, rid, n_res) torch tensors of a golden case."""
+    return (torch.from_numpy(c["X"]), torch.from_numpy(c["el"].astype(np.int64)),
+            torch.from_numpy(c["rid"].astype(np.int64)), int(c["n_res"]))
+
+
+@pytest.fixture(scope="session")
+def weights():
+    cache = {}
+
+    def get(tag):
+        if tag not in cache:
+            cache[tag] = load_weights(tag)
+        return cache[tag]
+    return get
+
+
+@pytest.fixture(scope="session")
+def cuda_models():
+    """pesto_b200.Model instances on cuda:0 with the shipped checkpoints (from the golden weight fixtures)."""
+    from pesto_b200.model import Model
+    cache = {}
+
+    def get(tag):
+        if tag not in cache:
+            m = Model(load_config(tag))
+            sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
+            m.load_state_dict(sd)
+            cache[tag] = m.eval().to("cuda")
+        return cache[tag]
+    return get

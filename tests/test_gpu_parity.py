@@ -1,0 +1,293 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors made by the unmodified
+reference, the CPU oracle on fresh seeded inputs, and size-independent properties at full size.
+
+Tolerances: kNN indices bit-exact (modulo permutations inside exact-distance tie groups, whose order torch.topk
+leaves unspecified); logits max-abs <= 1e-3 as BASELINE.json's north_star states (fp32 mode lands at ~1e-5).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_case, load_weights, case_tensors
+from oracle import pesto_oracle as O
+from oracle import scoring
+from pesto_b200.synth import synth_structure, one_hot_features, dense_membership, BASE_SEED
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3          # north_star tolerance
+FP32_EXPECTED = 2e-4      # what the fp32 path should actually achieve (fp32 re-association noise is ~1e-5)
+
+
+def cuda(*ts):
+    return [t.cuda() for t in ts]
+
+
+def run_case(model, c, mode="fp32", dense=True):
+    from pesto_b200.dataset import collate_batch_features
+    X, el, rid, n_res = case_tensors(c)
+    q0 = one_hot_features(el)
+    if "ids1" in c:
+        ids1 = torch.from_numpy(c["ids1"]).long()
+    else:
+        ids1 = collate_batch_features([[X, torch.from_numpy(c["ids0"]).long(), q0, dense_membership(rid, n_res)]])[1]
+    Xd, idsd, qd = cuda(X, ids1, q0)
+    if dense:
+        return model(Xd, idsd, qd, dense_membership(rid, n_res).cuda(), mode=mode)
+    return model(Xd, idsd, qd, rid.int().cuda(), n_res=n_res, mode=mode)
+
+
+# ------------------------------------------------------------------------------------------------- topology
+@pytest.mark.parametrize("name", ["2CUA_A", "1gpw_A", "1EWY", "tiny40", "synth517"])
+def test_knn_matches_reference(name):
+    from pesto_b200.data_encoding import extract_topology
+    c = load_case(name)
+    X = torch.from_numpy(c["X"])
+    ids, d, r, D, R = extract_topology(X.cuda(), 64)
+    ref = torch.from_numpy(c["ids0"]).long()
+    assert ids.dtype == torch.int64 and tuple(ids.shape) == tuple(ref.shape) and D is None and R is None
+    assert O.same_modulo_ties(ids.cpu(), ref, X)
+    # D_topk / R_topk: bit-exact against the oracle's dense recipe
+    oi, od, orr = O.extract_topology(X, 64)
+    assert torch.equal(ids.cpu(), oi)                       # same canonical (distance, index) order
+    assert torch.equal(d.cpu(), od)
+    assert torch.equal(r.cpu(), orr)
+
+
+def test_knn_synth8192_bit_exact():
+    from pesto_b200.data_encoding import extract_topology
+    g = dict(np.load(os.path.join(GOLDEN, "case_synth8192.npz")))
+    X, _, _ = synth_structure(8192, BASE_SEED)
+    ids = extract_topology(X.cuda(), 64)[0].cpu()
+    ref = torch.from_numpy(g["ids0"].astype(np.int64))
+    assert O.same_modulo_ties(ids, ref, X)
+    assert (ids == ref).float().mean().item() > 0.9999
+
+
+def test_knn_cpu_tensor_round_trip_and_small_k():
+    from pesto_b200.data_encoding import extract_topology
+    X, _, _ = synth_structure(300, 5)
+    ids_cpu = extract_topology(X, 16)[0]                     # CPU tensor in -> staged through the GPU -> CPU out
+    assert ids_cpu.device.type == "cpu" and ids_cpu.shape == (300, 16)
+    assert torch.equal(ids_cpu, O.extract_topology(X, 16)[0])
+
+
+def test_knn_duplicate_atoms_and_tiny_structures():
+    """Masked entries (D < 1e-2 -> + max D): duplicates and structures with <= 64 atoms exercise the exact path."""
+    from pesto_b200.data_encoding import extract_topology
+    X, _, _ = synth_structure(200, 11)
+    X[17] = X[3]                     # exact duplicate
+    X[50] = X[51] + 0.004            # closer than the 1e-2 mask
+    for n in (200, 66, 65, 64, 2):
+        Xn = X[:n].contiguous()
+        ids, d, r, _, _ = extract_topology(Xn.cuda(), 64)
+        oi, od, orr = O.extract_topology(Xn, 64)
+        assert torch.equal(ids.cpu(), oi), n
+        assert torch.equal(d.cpu(), od), n
+        assert torch.equal(torch.nan_to_num(r.cpu()), torch.nan_to_num(orr)), n
+
+
+def test_batch_topology_equals_collate_of_per_structure_knn():
+    from pesto_b200.data_encoding import batch_topology
+    c = load_case("batch3")
+    ids1 = batch_topology(torch.from_numpy(c["X"]).cuda(), [int(s) for s in c["sizes"]], 64)
+    assert torch.equal(ids1.cpu(), torch.from_numpy(c["ids1"]).long())
+
+
+# ------------------------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("name,tag", [("2CUA_A", "i_v4_1"), ("2CUA_A", "i_v4_0"), ("1gpw_A", "i_v4_1"),
+                                      ("1EWY", "i_v4_1"), ("tiny40", "i_v4_1"), ("tiny40", "i_v4_0"),
+                                      ("synth517", "i_v4_1"), ("batch3", "i_v4_1"), ("batch3", "i_v4_0"),
+                                      ("stale257", "i_v4_0")])
+def test_logits_match_reference(cuda_models, name, tag):
+    c = load_case(name)
+    z = run_case(cuda_models(tag), c).cpu()
+    ref = torch.from_numpy(c[f"z_{tag}"])
+    assert z.shape == ref.shape
+    err = (z - ref).abs().max().item()
+    assert err <= LOGIT_TOL, err
+    assert err <= FP32_EXPECTED, err
+
+
+def test_published_probabilities(cuda_models):
+    """examples/*_i{0..4}.pdb of the reference repo: sigmoid(z) to the 2 decimals of the b-factor column."""
+    for name in ("2CUA_A", "1gpw_A"):
+        c = load_case(name)
+        p = torch.sigmoid(run_case(cuda_models("i_v4_1"), c)).cpu().numpy()
+        assert np.abs(p - c["published_prob"]).max() <= 0.0051
+
+
+def test_sparse_residue_index_equals_dense_membership(cuda_models):
+    c = load_case("batch3")
+    m = cuda_models("i_v4_0")
+    assert torch.equal(run_case(m, c, dense=True), run_case(m, c, dense=False))
+
+
+def test_unsorted_residue_index(cuda_models):
+    """Atoms of a residue need not be contiguous: permute the membership columns' atoms via a shuffled rid."""
+    c = load_case("synth517")
+    m = cuda_models("i_v4_0")
+    X, el, rid, n_res = case_tensors(c)
+    g = torch.Generator().manual_seed(3)
+    rid2 = rid[torch.randperm(rid.shape[0], generator=g)]
+    n_res2 = int(rid2.max()) + 1
+    from pesto_b200.dataset import collate_batch_features
+    q0 = one_hot_features(el)
+    ids1 = collate_batch_features([[X, torch.from_numpy(c["ids0"]).long(), q0, dense_membership(rid2, n_res2)]])[1]
+    z = m(X.cuda(), ids1.cuda(), q0.cuda(), dense_membership(rid2, n_res2).cuda()).cpu()
+    zo = O.forward(load_weights("i_v4_0"), X, ids1, q0, rid2, n_res2)
+    assert (z - zo).abs().max().item() <= FP32_EXPECTED
+
+
+def test_per_layer_taps(cuda_models):
+    """Layer-by-layer (q, p) against forward hooks on the reference's model.sum[L], through the staged C ABI."""
+    from pesto_b200 import _lib
+    from pesto_b200.dataset import collate_batch_features
+    lib = _lib.load()
+    c = load_case("2CUA_A")
+    tag = "i_v4_1"
+    model = cuda_models(tag)
+    h = model._handle(0)
+    X, el, rid, n_res = case_tensors(c)
+    q0 = one_hot_features(el)
+    ids1 = collate_batch_features([[X, torch.from_numpy(c["ids0"]).long(), q0, dense_membership(rid, n_res)]])[1]
+    n = X.shape[0]
+    Xd, idsd, qd = cuda(X, ids1, q0)
+    st = [torch.empty((n + 1, 128), device="cuda") for _ in range(2)]
+    ids32 = torch.empty((n, 64), dtype=torch.int32, device="cuda")
+    geom = torch.empty((n, 64, 4), device="cuda")
+    scratch = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    node = torch.empty(lib.pesto_node_scratch_bytes(n), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.pesto_prologue(h, Xd.data_ptr(), idsd.data_ptr(), 64, qd.data_ptr(), n, st[0].data_ptr(),
+                                  ids32.data_ptr(), geom.data_ptr(), scratch.data_ptr(), None), "prologue")
+    q = torch.empty((n + 1, 32), device="cuda")
+    p = torch.empty((n + 1, 3, 32), device="cuda")
+    tap_layers = sorted(int(k.split("_L")[1].split("_")[0]) for k in c if k.startswith(f"tap_{tag}_") and k.endswith("_q"))
+    cur = 0
+    for layer in range(lib.pesto_model_num_layers(h)):
+        _lib.check(lib.pesto_state_update(h, layer, n, ids32.data_ptr(), geom.data_ptr(), st[cur].data_ptr(),
+                                          st[1 - cur].data_ptr(), node.data_ptr(), 0, None), "state_update")
+        cur = 1 - cur
+        if layer in tap_layers:
+            _lib.check(lib.pesto_unpack_state(st[cur].data_ptr(), n, q.data_ptr(), p.data_ptr(), None), "unpack")
+            eq = (q.cpu() - torch.from_numpy(c[f"tap_{tag}_L{layer}_q"])).abs().max().item()
+            ep = (p.cpu() - torch.from_numpy(c[f"tap_{tag}_L{layer}_p"])).abs().max().item()
+            assert eq <= 2e-4 and ep <= 5e-4, (layer, eq, ep)
+            assert float(q[0].abs().max()) == 0.0 and float(p[0].abs().max()) == 0.0     # sink row stays zero
+
+
+def test_benchmark_table_53_structures(cuda_models):
+    """BASELINE config 2: all 53 pdbs_test structures.  Logits within tolerance of the reference and the 53 x 8
+    published metrics (interface_ppi_benchmark.ipynb:168-220) reproduced string-identically."""
+    from pesto_b200.data_encoding import extract_topology
+    from pesto_b200.dataset import collate_batch_features
+    g = dict(np.load(os.path.join(GOLDEN, "pdbs_test_53.npz")))
+    model = cuda_models("i_v4_1")
+    aoff = np.concatenate([[0], np.cumsum(g["sizes"])])
+    roff = np.concatenate([[0], np.cumsum(g["n_res"])])
+    worst, mismatched = 0.0, []
+    for i, key in enumerate(g["keys"]):
+        X = torch.from_numpy(g["X"][aoff[i]:aoff[i + 1]]).cuda()
+        el = torch.from_numpy(g["el"][aoff[i]:aoff[i + 1]].astype(np.int64))
+        rid = torch.from_numpy(g["rid"][aoff[i]:aoff[i + 1]].astype(np.int64))
+        M = dense_membership(rid, int(g["n_res"][i])).cuda()
+        q = one_hot_features(el).cuda()
+        ids0 = extract_topology(X, 64)[0]
+        Xc, ids1, qc, Mc = collate_batch_features([[X, ids0, q, M]])
+        z = model(Xc, ids1, qc, Mc.float()).cpu()
+        worst = max(worst, (z - torch.from_numpy(g["z_i_v4_1"][roff[i]:roff[i + 1]])).abs().max().item())
+        line = scoring.table_line(str(key), g["y"][roff[i]:roff[i + 1]], torch.sigmoid(z[:, 0]).numpy())
+        if line != str(g["table_published"][i]):
+            mismatched.append((line, str(g["table_published"][i])))
+    assert worst <= LOGIT_TOL, worst
+    assert not mismatched, mismatched[:3]
+
+
+def test_synth8192_full_size(cuda_models):
+    """Full-size (N = 8192, k = 64, i_v4_1) against the reference's logits (75 s of CPU, stored)."""
+    from pesto_b200.data_encoding import extract_topology
+    g = dict(np.load(os.path.join(GOLDEN, "case_synth8192.npz")))
+    X, el, rid = synth_structure(8192, BASE_SEED)
+    Xd = X.cuda()
+    ids1 = extract_topology(Xd, 64)[0] + 1
+    z = cuda_models("i_v4_1")(Xd, ids1, one_hot_features(el).cuda(), rid.int().cuda(), n_res=1024).cpu()
+    err = (z - torch.from_numpy(g["z_i_v4_1"])).abs().max().item()
+    assert err <= LOGIT_TOL, err
+
+
+# ------------------------------------------------------------------------------------------------- properties
+def test_batched_equals_separate(cuda_models):
+    """Structures are independent: a collated batch gives the same logits as separate forwards."""
+    from pesto_b200.data_encoding import extract_topology
+    from pesto_b200.dataset import collate_batch_features
+    model = cuda_models("i_v4_0")
+    parts, zs = [], []
+    for k, n in enumerate((700, 1301, 96)):
+        X, el, rid = synth_structure(n, 100 + k)
+        Xd = X.cuda()
+        item = [Xd, extract_topology(Xd, 64)[0], one_hot_features(el).cuda(), dense_membership(rid).cuda()]
+        parts.append(item)
+        zs.append(model(*collate_batch_features([item])))
+    zb = model(*collate_batch_features(parts))
+    assert (zb - torch.cat(zs)).abs().max().item() <= 1e-4
+
+
+def test_rigid_motion_invariance_full_size(cuda_models):
+    """Logits are invariant to rotation + translation of the input cloud (N = 8192)."""
+    from pesto_b200.data_encoding import extract_topology
+    model = cuda_models("i_v4_1")
+    X, el, rid = synth_structure(8192, 77)
+    q0 = one_hot_features(el).cuda()
+    ridd = rid.int().cuda()
+    Xd = X.cuda()
+    ids1 = extract_topology(Xd, 64)[0] + 1
+    z0 = model(Xd, ids1, q0, ridd, n_res=1024)
+    g = torch.Generator().manual_seed(1)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    X2 = (X.double() @ Q + torch.tensor([12.5, -40.0, 7.25], dtype=torch.float64)).float().cuda()
+    z1 = model(X2, ids1, q0, ridd, n_res=1024)      # same topology: rigid motion preserves neighbour sets
+    assert torch.isfinite(z0).all()
+    assert (z0 - z1).abs().max().item() <= 2e-3
+
+
+def test_atom_permutation_equivariance(cuda_models):
+    """Relabelling atoms (and their ids) leaves the per-residue logits unchanged."""
+    from pesto_b200.data_encoding import extract_topology
+    model = cuda_models("i_v4_0")
+    X, el, rid = synth_structure(1500, 31)
+    g = torch.Generator().manual_seed(2)
+    perm = torch.randperm(1500, generator=g)
+    n_res = int(rid.max()) + 1
+
+    def fwd(X, el, rid):
+        Xd = X.cuda()
+        ids1 = extract_topology(Xd, 64)[0] + 1
+        return model(Xd, ids1, one_hot_features(el).cuda(), rid.int().cuda(), n_res=n_res)
+    za, zb = fwd(X, el, rid), fwd(X[perm].contiguous(), el[perm], rid[perm])
+    assert (za - zb).abs().max().item() <= 2e-4
+
+
+# ------------------------------------------------------------------------------------------------- errors
+def test_bad_inputs_raise_or_poison(cuda_models):
+    from pesto_b200 import _lib
+    model = cuda_models("i_v4_0")
+    X, el, rid = synth_structure(128, 9)
+    q0 = one_hot_features(el).cuda()
+    M = dense_membership(rid).cuda()
+    ids = torch.randint(0, 129, (128, 64)).cuda()
+    with pytest.raises(ValueError):
+        model(X.cuda(), ids[:100], q0, M)
+    with pytest.raises(ValueError):
+        model(X.cuda(), ids, q0[:, :20], M)
+    with pytest.raises(_lib.PestoError):
+        model(X.cuda(), ids[:, :32].contiguous(), q0, M)           # fewer columns than the largest nn
+    bad = ids.clone()
+    bad[5, 5] = 4000                                               # out of range -> NaN logits, no crash
+    assert torch.isnan(model(X.cuda(), bad, q0, M)).all()
+    M2 = M.clone()
+    M2[3] = 0.0                                                    # not one-hot -> NaN logits
+    assert torch.isnan(model(X.cuda(), ids, q0, M2)).all()
+    assert torch.isfinite(model(X.cuda(), ids, q0, M)).all()       # and the model still works afterwards

@@ -1,0 +1,118 @@
+"""Host-side logic and the C-ABI surface.  CPU only: no compute call is made without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, load_case, load_weights, load_config
+from oracle import pesto_oracle as O
+from pesto_b200 import _lib
+from pesto_b200.dataset import collate_batch_features
+from pesto_b200.model import Model
+from pesto_b200.sharding import lpt_partition
+from pesto_b200.synth import synth_structure, one_hot_features, dense_membership, interfaceome_sizes
+
+
+@pytest.fixture(scope="module")
+def library():
+    if not os.path.exists(_lib.LIB_PATH):
+        from pesto_b200.build import build_library
+        build_library()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(library):
+    header = open(os.path.join(REPO, "include", "pesto_b200.h")).read()
+    declared = set(re.findall(r"\b(pesto_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(library, name), f"libpesto_b200.so does not export {name}"
+    assert library.pesto_abi_version() == 1
+
+
+def test_size_queries_need_no_gpu(library):
+    assert library.pesto_forward_workspace_bytes(8192, 1024) > 8192 * 128 * 4 * 2
+    assert library.pesto_knn_scratch_bytes(100, 3) >= 100 * 4
+    assert library.pesto_forward_workspace_bytes(0, 0) == 0
+
+
+def test_model_create_rejects_bad_layers(library):
+    nn = np.array([8, 12], dtype=np.int32)
+    assert not library.pesto_model_create(2, nn.ctypes.data, 30)
+    assert b"nn=12" in library.pesto_last_error()
+
+
+@pytest.mark.parametrize("tag", ["i_v4_1", "i_v4_0"])
+def test_model_accepts_reference_state_dict(tag):
+    """load_state_dict with the checkpoint's own keys, strict."""
+    m = Model(load_config(tag))
+    sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert len(sd) == {"i_v4_1": 1081, "i_v4_0": 553}[tag]
+    if tag == "i_v4_1":      # parameter count printed by the reference's training log (slurm-731740.out:1387)
+        assert sum(p.numel() for p in m.parameters()) == 1474957
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    m = Model(load_config("i_v4_0"))
+    X, el, rid = synth_structure(64, 1)
+    with pytest.raises(_lib.PestoError):
+        m(X, torch.zeros((64, 64), dtype=torch.long), one_hot_features(el), dense_membership(rid))
+    from pesto_b200.data_encoding import extract_topology
+    with pytest.raises(_lib.PestoError):
+        extract_topology(X, 64)
+
+
+def test_collate_matches_oracle_and_golden():
+    c = load_case("batch3")
+    sizes = c["sizes"]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = torch.from_numpy(c["X"])
+    rid = torch.from_numpy(c["rid"].astype(np.int64))
+    el = torch.from_numpy(c["el"].astype(np.int64))
+    parts, oparts = [], []
+    r0 = 0
+    for i in range(len(sizes)):
+        sl = slice(off[i], off[i + 1])
+        r_local = rid[sl] - r0
+        n_res = int(r_local.max()) + 1
+        ids0 = torch.from_numpy(c[f"ids0_{i}"]).long()
+        parts.append([X[sl], ids0, one_hot_features(el[sl]), dense_membership(r_local, n_res)])
+        oparts.append((X[sl], ids0, one_hot_features(el[sl]), r_local, n_res))
+        r0 += n_res
+    Xc, ids1, q, M = collate_batch_features(parts)
+    assert torch.equal(ids1, torch.from_numpy(c["ids1"]).long())          # the reference's collate output
+    assert torch.equal(M.argmax(1), rid) and M.shape == (X.shape[0], int(c["n_res"]))
+    assert torch.equal(M.sum(1), torch.ones(X.shape[0]))
+    Xo, ids1o, qo, rido, R = O.collate(oparts)
+    assert torch.equal(ids1o, ids1) and torch.equal(rido, rid) and R == int(c["n_res"]) and torch.equal(Xo, Xc)
+    _, _, _, Ms = collate_batch_features(parts, sparse_membership=True)
+    assert torch.equal(Ms.long(), rid)
+
+
+def test_synth_is_deterministic_and_protein_like():
+    X1, el1, rid1 = synth_structure(1024, 20230419)
+    X2, el2, rid2 = synth_structure(1024, 20230419)
+    assert torch.equal(X1, X2) and torch.equal(el1, el2) and torch.equal(rid1, rid2)
+    d = torch.cdist(X1.double(), X1.double())
+    d.fill_diagonal_(1e9)
+    assert d.min().item() > 0.05                     # nothing inside the 1e-2 mask of extract_topology
+    nn64 = d.sort(1)[0][:, 63].mean().item()
+    assert 6.0 < nn64 < 9.0                          # real structures: 7.6 A to the 64th neighbour
+    sizes = interfaceome_sizes(1000)
+    assert sizes.min() >= 16 and sizes.max() <= 2700
+
+
+def test_lpt_partition_balances_cost():
+    rng = np.random.default_rng(0)
+    costs = rng.integers(100, 20000, size=500)
+    for g in (1, 2, 4, 8):
+        shards = lpt_partition(costs, g)
+        assert sorted(i for s in shards for i in s) == list(range(500))
+        loads = [sum(int(costs[i]) for i in s) for s in shards]
+        assert max(loads) <= 1.02 * (sum(loads) / g) + costs.max()

@@ -1,0 +1,106 @@
+"""The CPU oracle (oracle/) against outputs of the UNMODIFIED reference (tests/golden/*.npz).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case, load_weights, case_tensors
+from oracle import pesto_oracle as O
+from oracle import scoring
+from pesto_b200.synth import one_hot_features
+
+TOL = 1e-4   # fp32 re-association noise between two CPU formulations (observed ~1e-5)
+
+
+def oracle_forward(tag, c, taps=None):
+    X, el, rid, n_res = case_tensors(c)
+    if "ids1" in c:
+        ids1 = torch.from_numpy(c["ids1"]).long()
+    else:
+        ids1 = O.collate([(X, torch.from_numpy(c["ids0"]).long(), one_hot_features(el), rid, n_res)])[1]
+    return O.forward(load_weights(tag), X, ids1, one_hot_features(el), rid, n_res, taps=taps)
+
+
+@pytest.mark.parametrize("name", ["2CUA_A", "1gpw_A", "1EWY", "tiny40", "synth517", "stale257"])
+def test_topology_matches_reference(name):
+    c = load_case(name)
+    if name == "stale257":
+        pytest.skip("ids of this case are deliberately stale")
+    X = torch.from_numpy(c["X"])
+    ids, d, r = O.extract_topology(X, 64)
+    ref = torch.from_numpy(c["ids0"]).long()
+    assert ids.shape == ref.shape
+    assert O.same_modulo_ties(ids, ref, X)
+    # prefix sets used by the layers (nn = 8/16/32/64) are identical wherever no tie straddles the boundary
+    frac_equal = (ids == ref).float().mean().item()
+    assert frac_equal > 0.999
+
+
+def test_topology_batch_case():
+    c = load_case("batch3")
+    sizes = c["sizes"]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    X = torch.from_numpy(c["X"])
+    for i in range(len(sizes)):
+        Xi = X[off[i]:off[i + 1]]
+        ids, _, _ = O.extract_topology(Xi, 64)
+        assert O.same_modulo_ties(ids, torch.from_numpy(c[f"ids0_{i}"]).long(), Xi)
+
+
+@pytest.mark.parametrize("name,tag", [("tiny40", "i_v4_1"), ("tiny40", "i_v4_0"), ("batch3", "i_v4_0"),
+                                      ("stale257", "i_v4_0"), ("synth517", "i_v4_0")])
+def test_forward_matches_reference(name, tag):
+    c = load_case(name)
+    L = len(O.layer_nn(load_weights(tag)))
+    taps = {0: None, L - 1: None} if f"tap_{tag}_L0_q" in c else None
+    z = oracle_forward(tag, c, taps)
+    assert (z - torch.from_numpy(c[f"z_{tag}"])).abs().max().item() < TOL
+    if taps:
+        for li in taps:
+            assert (taps[li][0] - torch.from_numpy(c[f"tap_{tag}_L{li}_q"])).abs().max().item() < TOL
+            assert (taps[li][1] - torch.from_numpy(c[f"tap_{tag}_L{li}_p"])).abs().max().item() < 5e-4
+
+
+def test_forward_real_structure_and_published_probabilities():
+    """examples/issue_19_04_2023/2CUA_A: reference logits, per-layer taps and the published *_i{0..4}.pdb b-factors."""
+    c = load_case("2CUA_A")
+    taps = {0: None, 8: None, 31: None}
+    z = oracle_forward("i_v4_1", c, taps)
+    assert (z - torch.from_numpy(c["z_i_v4_1"])).abs().max().item() < TOL
+    for li in taps:
+        assert (taps[li][0] - torch.from_numpy(c[f"tap_i_v4_1_L{li}_q"])).abs().max().item() < 2e-4
+        assert (taps[li][1] - torch.from_numpy(c[f"tap_i_v4_1_L{li}_p"])).abs().max().item() < 5e-4
+    p = torch.sigmoid(z).numpy()
+    assert np.abs(p - c["published_prob"]).max() <= 0.00501     # b-factors carry 2 decimals
+
+
+def test_scoring_reproduces_published_table_from_reference_logits():
+    """oracle.scoring on the stored reference logits reproduces all 53 published lines
+    (interface_ppi_benchmark.ipynb:168-220)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "pdbs_test_53.npz")))
+    roff = np.concatenate([[0], np.cumsum(g["n_res"])])
+    for i, key in enumerate(g["keys"]):
+        z = g["z_i_v4_1"][roff[i]:roff[i + 1]]
+        y = g["y"][roff[i]:roff[i + 1]]
+        p = torch.sigmoid(torch.from_numpy(z[:, 0])).numpy()
+        assert scoring.table_line(str(key), y, p) == str(g["table_published"][i])
+
+
+@pytest.mark.slow
+def test_oracle_reproduces_published_table_end_to_end():
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "pdbs_test_53.npz")))
+    W = load_weights("i_v4_1")
+    aoff = np.concatenate([[0], np.cumsum(g["sizes"])])
+    roff = np.concatenate([[0], np.cumsum(g["n_res"])])
+    for i, key in enumerate(g["keys"]):
+        X = torch.from_numpy(g["X"][aoff[i]:aoff[i + 1]])
+        el = torch.from_numpy(g["el"][aoff[i]:aoff[i + 1]].astype(np.int64))
+        rid = torch.from_numpy(g["rid"][aoff[i]:aoff[i + 1]].astype(np.int64))
+        ids0, _, _ = O.extract_topology(X, 64)
+        Xc, ids1, q0, ridc, R = O.collate([(X, ids0, one_hot_features(el), rid, int(g["n_res"][i]))])
+        z = O.forward(W, Xc, ids1, q0, ridc, R)
+        p = torch.sigmoid(z[:, 0]).numpy()
+        assert scoring.table_line(str(key), g["y"][roff[i]:roff[i + 1]], p) == str(g["table_published"][i])
