@@ -108,6 +108,13 @@ int    pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const 
                           const float *geom, const float *state_in, float *state_out,
                           void *node_scratch, int mode, void *stream);
 
+/* Measurement aid for bench.py's roofline: same as pesto_state_update, but brackets the per-atom (node) kernel
+ * and the fused per-edge kernel with CUDA events on `stream`, waits for them and returns both durations in ms. */
+int    pesto_state_update_timed(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32,
+                                const float *geom, const float *state_in, float *state_out,
+                                void *node_scratch, int mode, void *stream,
+                                float *ms_node_host, float *ms_edge_host);
+
 /* dense one-hot membership M[n_atoms, n_res] (fp32, the reference's 4th forward argument) -> residue
  * column per atom.  flags[0] is set non-zero on device if some row is not one-hot. */
 int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream);

@@ -29,7 +29,7 @@ int check_cuda(cudaError_t e, const char *what) {
 
 int launch_state_update_tc(const float *layer_w, const void *layer_tc, int nn, int n_atoms, const int32_t *ids32,
                            const float *geom, const float *state_in, float *state_out, float *node_scratch, int mode,
-                           cudaStream_t st);
+                           cudaStream_t st, cudaEvent_t *ev);
 size_t tc_layer_bytes();
 void pack_tc_layer(const float *layer_blob_host, void *dst_host);
 
@@ -318,8 +318,9 @@ size_t pesto_node_scratch_bytes(int n_atoms) {
     return ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE) * sizeof(float);
 }
 
-int pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
-                       const float *state_in, float *state_out, void *node_scratch, int mode, void *stream) {
+static int state_update_impl(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
+                             const float *state_in, float *state_out, void *node_scratch, int mode, void *stream,
+                             cudaEvent_t *ev) {
     if (!valid_model(m, "pesto_state_update")) return PESTO_ESTATE;
     if (layer < 0 || layer >= m->n_layers || n_atoms < 1 || !ids32 || !geom || !state_in || !state_out || !node_scratch ||
         state_in == state_out) {
@@ -328,12 +329,33 @@ int pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const int
     }
     if (mode == PESTO_MODE_FP32)
         return launch_state_update_fp32(m->layer(layer), m->nn[layer], n_atoms, ids32, geom, state_in, state_out,
-                                        (float *)node_scratch, (cudaStream_t)stream);
+                                        (float *)node_scratch, (cudaStream_t)stream, ev);
     if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16)
         return launch_state_update_tc(m->layer(layer), m->layer_tc(layer), m->nn[layer], n_atoms, ids32, geom, state_in,
-                                      state_out, (float *)node_scratch, mode, (cudaStream_t)stream);
+                                      state_out, (float *)node_scratch, mode, (cudaStream_t)stream, ev);
     set_error("pesto_state_update: unknown mode %d", mode);
     return PESTO_EINVAL;
+}
+
+int pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
+                       const float *state_in, float *state_out, void *node_scratch, int mode, void *stream) {
+    return state_update_impl(m, layer, n_atoms, ids32, geom, state_in, state_out, node_scratch, mode, stream, nullptr);
+}
+
+int pesto_state_update_timed(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
+                             const float *state_in, float *state_out, void *node_scratch, int mode, void *stream,
+                             float *ms_node_host, float *ms_edge_host) {
+    cudaEvent_t ev[3];
+    for (int i = 0; i < 3; ++i) PESTO_CUDA(cudaEventCreate(&ev[i]));
+    int rc = state_update_impl(m, layer, n_atoms, ids32, geom, state_in, state_out, node_scratch, mode, stream, ev);
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventSynchronize(ev[2]), "cudaEventSynchronize");
+    float a = 0.f, b = 0.f;
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventElapsedTime(&a, ev[0], ev[1]), "cudaEventElapsedTime");
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventElapsedTime(&b, ev[1], ev[2]), "cudaEventElapsedTime");
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+    if (ms_node_host) *ms_node_host = a;
+    if (ms_edge_host) *ms_edge_host = b;
+    return rc;
 }
 
 int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream) {

@@ -121,7 +121,9 @@ int launch_prologue(const float *head_w, int q0_dim, const float *X, const int64
                     const float *q0, int n_atoms, float *state, int32_t *ids32, float *geom,
                     void *scratch4, cudaStream_t st);
 int launch_state_update_fp32(const float *layer_w, int nn, int n_atoms, const int32_t *ids32, const float *geom,
-                             const float *state_in, float *state_out, float *node_scratch, cudaStream_t st);
+                             const float *state_in, float *state_out, float *node_scratch, cudaStream_t st,
+                             cudaEvent_t *ev = nullptr);
+int launch_node(const float *layer_w, int n_atoms, const float *state_in, float *node_scratch, cudaStream_t st);
 int launch_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, cudaStream_t st);
 int launch_pool_decode(const float *head_w, const float *state, const int32_t *rid, int n_atoms, int n_res,
                        float *z, void *scratch, const int32_t *poison, cudaStream_t st);

@@ -433,22 +433,37 @@ int launch_edge(const float *lw, int n_atoms, const int32_t *ids32, const float 
 
 }  // namespace
 
-int launch_state_update_fp32(const float *lw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
-                             const float *state_in, float *state_out, float *node_scratch, cudaStream_t st) {
+int launch_node(const float *lw, int n_atoms, const float *state_in, float *node_scratch, cudaStream_t st) {
     const int n_rows = n_atoms + 1;
     float *nodeT = node_scratch;
     float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
     node_kernel<<<(n_rows + NODE_ATOMS - 1) / NODE_ATOMS, 128, 0, st>>>(lw, state_in, n_rows, nodeT, nodeC);
     PESTO_CUDA(cudaGetLastError());
+    return PESTO_OK;
+}
+
+// `ev` (optional, 3 events): recorded before the node kernel, between node and edge kernel, after the edge kernel
+int launch_state_update_fp32(const float *lw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
+                             const float *state_in, float *state_out, float *node_scratch, cudaStream_t st,
+                             cudaEvent_t *ev) {
+    const int n_rows = n_atoms + 1;
+    float *nodeT = node_scratch;
+    float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
+    if (ev) PESTO_CUDA(cudaEventRecord(ev[0], st));
+    int rc = launch_node(lw, n_atoms, state_in, node_scratch, st);
+    if (rc != PESTO_OK) return rc;
+    if (ev) PESTO_CUDA(cudaEventRecord(ev[1], st));
     switch (nn) {
-        case 8:  return launch_edge<8>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 16: return launch_edge<16>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 32: return launch_edge<32>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 64: return launch_edge<64>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
+        case 8:  rc = launch_edge<8>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st); break;
+        case 16: rc = launch_edge<16>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st); break;
+        case 32: rc = launch_edge<32>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st); break;
+        case 64: rc = launch_edge<64>(lw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st); break;
         default:
             set_error("state_update: unsupported nn=%d (supported: 8, 16, 32, 64)", nn);
             return PESTO_EINVAL;
     }
+    if (rc == PESTO_OK && ev) PESTO_CUDA(cudaEventRecord(ev[2], st));
+    return rc;
 }
 
 }  // namespace pesto

@@ -27,7 +27,10 @@ def pytest_collection_modifyitems(config, items):
 
 
 def load_case(name):
-    return dict(np.load(os.path.join(GOLDEN, f"case_{name}.npz")))
+    c = dict(np.load(os.path.join(GOLDEN, f"case_{name}.npz")))
+    if "ids0" not in c and "ids0_0" in c and len(c["sizes"]) == 1:
+        c["ids0"] = c["ids0_0"]          # single-structure cases written through the multi-structure path
+    return c
 
 
 def load_weights(tag):

@@ -4,7 +4,7 @@
 GPU box, so its inputs/outputs are committed here as small .npz fixtures.
 
     python tests/golden/make_golden.py small      # weights + small cases (+ per-layer taps)   ~2 min
-    python tests/golden/make_golden.py bench53    # the 53 pdbs_test structures (config 2)      ~25 min
+    python tests/golden/make_golden.py bench53 bench53_ties   # the 53 pdbs_test structures (config 2)   ~25 min
     python tests/golden/make_golden.py synth8192  # synthetic N=8192 (config 3/4 shape)         ~3 min
 
 Nothing from the reference's sources is copied: the script imports it in place.
@@ -235,6 +235,28 @@ def part_bench53():
     print("bench53 done", time.time() - t0)
 
 
+def part_bench53_ties():
+    """torch.topk leaves the order inside exact-distance tie groups unspecified; the CUDA kernel and the oracle
+    use (distance, index).  Record the rows of the 53 structures where the reference's CPU topk order differs,
+    so that forward parity can be tested on exactly the neighbour lists the reference used."""
+    from oracle import pesto_oracle as O
+    path = os.path.join(HERE, "pdbs_test_53.npz")
+    g = dict(np.load(path))
+    aoff = np.concatenate([[0], np.cumsum(g["sizes"])])
+    st, rows, ids, straddle = [], [], [], []
+    for i in range(len(g["keys"])):
+        X = torch.from_numpy(g["X"][aoff[i]:aoff[i + 1]])
+        r = extract_topology(X, 64)[0]
+        o = O.extract_topology(X, 64)[0]
+        for row in (r != o).any(1).nonzero()[:, 0].tolist():
+            st.append(i); rows.append(row); ids.append(r[row].numpy().astype(np.int32))
+            straddle.append(any(set(r[row, :n].tolist()) != set(o[row, :n].tolist()) for n in (8, 16, 32, 64)))
+    g.update(tie_struct=np.array(st, np.int32), tie_row=np.array(rows, np.int32), tie_ids=np.stack(ids),
+             tie_straddles_prefix=np.array(straddle))
+    np.savez_compressed(path, **g)
+    print("tie rows:", len(rows), "straddling a prefix boundary:", int(np.sum(straddle)))
+
+
 def part_synth8192():
     t0 = time.time()
     model, cfg, _ = load_reference_model("i_v4_1")
@@ -254,4 +276,4 @@ def part_synth8192():
 if __name__ == "__main__":
     torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", os.cpu_count())))
     for part in sys.argv[1:]:
-        {"small": part_small, "bench53": part_bench53, "synth8192": part_synth8192}[part]()
+        {"small": part_small, "bench53": part_bench53, "bench53_ties": part_bench53_ties, "synth8192": part_synth8192}[part]()

