@@ -139,6 +139,12 @@ int    pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1
                      const float *q0, const float *M, const int32_t *rid, int n_atoms, int n_res,
                      float *z, void *workspace, size_t workspace_bytes, int mode, void *stream);
 
+/* Debug / self-test: D[128,N] = A[128,K] * B[N,K]^T on the tensor cores with exactly the operand staging of the
+ * fused kernel (A thread-per-row in TMEM, B K-major un-swizzled in shared memory); split != 0 selects the 3-term
+ * split-bf16 product.  lbo / sbo < 0 and idesc == 0 select the library's own descriptor values. */
+int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int N, int split,
+                           int lbo, int sbo, int idesc, void *stream);
+
 /* number of kernels one pesto_forward / pesto_knn call launches (for bench.py's gpu_launches) */
 int pesto_forward_launch_count(const pesto_model_t *m, int dense_m);
 int pesto_knn_launch_count(void);

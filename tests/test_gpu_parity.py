@@ -321,3 +321,68 @@ def test_bad_inputs_raise_or_poison(cuda_models):
     M2[3] = 0.0                                                    # not one-hot -> NaN logits
     assert torch.isnan(model(X.cuda(), ids, q0, M2)).all()
     assert torch.isfinite(model(X.cuda(), ids, q0, M)).all()       # and the model still works afterwards
+
+
+# ------------------------------------------------------------------------------------------------- tensor-core modes
+def _staged(model, c):
+    """prologue through the staged C ABI; returns what pesto_state_update needs."""
+    from pesto_b200 import _lib
+    from pesto_b200.dataset import collate_batch_features
+    lib = _lib.load()
+    X, el, rid, n_res = case_tensors(c)
+    q0 = one_hot_features(el)
+    ids1 = collate_batch_features([[X, torch.from_numpy(c["ids0"]).long(), q0, dense_membership(rid, n_res)]])[1]
+    n = X.shape[0]
+    Xd, idsd, qd = cuda(X, ids1, q0)
+    h = model._handle(0)
+    st0 = torch.empty((n + 1, 128), device="cuda")
+    ids32 = torch.empty((n, 64), dtype=torch.int32, device="cuda")
+    geom = torch.empty((n, 64, 4), device="cuda")
+    scratch = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    node = torch.empty(lib.pesto_node_scratch_bytes(n), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.pesto_prologue(h, Xd.data_ptr(), idsd.data_ptr(), 64, qd.data_ptr(), n, st0.data_ptr(),
+                                  ids32.data_ptr(), geom.data_ptr(), scratch.data_ptr(), None), "prologue")
+    return lib, h, n, st0, ids32, geom, node
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-4), (2, 6e-2)])
+def test_tensor_core_layer_against_fp32_layer(cuda_models, mode, tol):
+    """Every layer of i_v4_1 (nn = 8, 16, 32, 64): the tcgen05 edge kernel against the FFMA kernel on the same
+    input state (states grow to |q| ~ 40, so the tolerance is relative to the state's magnitude)."""
+    from pesto_b200 import _lib
+    model = cuda_models("i_v4_1")
+    lib, h, n, st0, ids32, geom, node = _staged(model, load_case("2CUA_A"))
+    cur = st0
+    for layer in range(lib.pesto_model_num_layers(h)):
+        ref = torch.empty_like(cur)
+        out = torch.empty_like(cur)
+        _lib.check(lib.pesto_state_update(h, layer, n, ids32.data_ptr(), geom.data_ptr(), cur.data_ptr(), ref.data_ptr(),
+                                          node.data_ptr(), 0, None), "fp32 layer")
+        _lib.check(lib.pesto_state_update(h, layer, n, ids32.data_ptr(), geom.data_ptr(), cur.data_ptr(), out.data_ptr(),
+                                          node.data_ptr(), mode, None), "tc layer")
+        torch.cuda.synchronize()
+        scale = max(1.0, ref.abs().max().item())
+        err = (out - ref).abs().max().item() / scale
+        assert err <= tol, (layer, err, scale)
+        cur = ref
+
+
+@pytest.mark.parametrize("name,tag", [("2CUA_A", "i_v4_1"), ("1gpw_A", "i_v4_1"), ("tiny40", "i_v4_1"),
+                                      ("batch3", "i_v4_0"), ("synth517", "i_v4_1"), ("1EWY", "i_v4_1")])
+def test_logits_bf16x3_within_north_star_tolerance(cuda_models, name, tag):
+    """Parity mode on the tensor cores: 3-term split bf16, logits within 1e-3 of the reference."""
+    c = load_case(name)
+    z = run_case(cuda_models(tag), c, mode="bf16x3").cpu()
+    err = (z - torch.from_numpy(c[f"z_{tag}"])).abs().max().item()
+    assert err <= LOGIT_TOL, err
+
+
+def test_logits_bf16_speed_mode_reports_its_error(cuda_models):
+    """Single-pass bf16 cannot meet 1e-3 (~0.14 on logits); it must stay a sane approximation."""
+    c = load_case("2CUA_A")
+    z = run_case(cuda_models("i_v4_1"), c, mode="bf16").cpu()
+    ref = torch.from_numpy(c["z_i_v4_1"])
+    err = (z - ref).abs().max().item()
+    perr = (torch.sigmoid(z) - torch.sigmoid(ref)).abs().max().item()
+    print(f"bf16 speed mode: max|dz| = {err:.3e}, max|dp| = {perr:.3e}")
+    assert err < 1.0 and perr < 0.1
