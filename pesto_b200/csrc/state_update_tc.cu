@@ -108,7 +108,7 @@ namespace {
 
 __device__ int g_tc_watchdog = 0;     // != 0: a tensor-core stage timed out (stage id), see mbar_wait
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;     // 8 warps per tile: two column groups x four TMEM lane quarters
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr uint32_t TM_COLS = 256;     // TMEM columns per CTA: X = [0,128), Y = [128,256)
 constexpr uint32_t TX = 0, TY = 128;
@@ -184,26 +184,31 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
     }
 }
 
+// Column-split mapping: a tile (128 edges) is worked on by 8 warps.  Warps 0-3 (group 0) and warps 4-7 (group 1)
+// both map thread -> edge/TMEM lane 32*(warp%4)+lane, and each group handles half of the columns of every
+// stage.  This doubles the warps per SM (2 CTAs x 8 warps) at half the registers per thread, which is what hides
+// the gather / TMEM / shuffle latencies.
 template <int NN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ tcw, int n_atoms,
                const int32_t *__restrict__ ids32, const float4 *__restrict__ geom, const float *__restrict__ state_in,
                const float *__restrict__ nodeT, const float *__restrict__ nodeC, float *__restrict__ state_out) {
-    constexpr int TA = TC_THREADS / NN;             // atoms per tile
+    constexpr int TA = 128 / NN;                    // atoms per tile
     constexpr int SEG = NN < 32 ? NN : 32;          // lanes of one atom inside a warp
     constexpr int APW = 32 / SEG;                   // atoms per warp
     constexpr int EPL = 32 / SEG;                   // reduced elements per lane and 32-vector
-    constexpr int WPA = NN / SEG;                   // warps per atom (2 for nn = 64)
+    constexpr int WPA = NN / SEG;                   // warps (of one group) per atom: 2 for nn = 64
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *img = smem_raw;                                      // weight images + biases
     const float *b2 = reinterpret_cast<const float *>(img + tcimg::BIAS);
     const float *b3 = b2 + 128;
-    float *Zs = reinterpret_cast<float *>(img + tcimg::TOTAL);          // [4 warps][APW][256]
-    float *red = Zs + 4 * APW * 256;                                    // [4][8]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 32);
+    float *Zs = reinterpret_cast<float *>(img + tcimg::TOTAL);          // [4 lane quarters][APW][256]
+    float *red = Zs + 4 * APW * 256;                                    // [2 groups][4][8]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 64);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp >> 2, quarter = warp & 3;       // column group, TMEM lane quarter
     if (warp == 0) tc::tmem_alloc(tmem_slot, TM_COLS);
     if (tid == 0) {
         tc::mbar_init(bar, 1);
@@ -211,20 +216,22 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
     }
     for (int u = tid; u < tcimg::TOTAL / 16; u += TC_THREADS)
         reinterpret_cast<uint4 *>(img)[u] = __ldg(reinterpret_cast<const uint4 *>(tcw) + u);
-    if (blockIdx.x == 0) state_out[tid] = 0.f;       // sink row stays zero (src/model_operations.py:239-240)
+    if (blockIdx.x == 0 && tid < SR) state_out[tid] = 0.f;   // sink row stays zero (src/model_operations.py:239-240)
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
-    const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
     const uint32_t img_hi = tc::smem_u32(img), img_lo = img_hi + tcimg::IMG;
     uint32_t phase = 0;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
+    float *redg = red + grp * 32;
 
     const int n_tiles = (n_atoms + TA - 1) / TA;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int a_loc = tid / NN, k = tid % NN;
+        const int e = tid & 127;                                   // edge slot inside the tile = TMEM lane
+        const int a_loc = e / NN, k = e % NN;
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
         const int j = ids32[(size_t)i * KMAX + k];
         const float4 g = geom[(size_t)i * KMAX + k];
@@ -234,47 +241,35 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         const float *tJ = nodeT + (size_t)j * NODE_T_STRIDE;
 
         // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d] -> TMEM (Y)
+        // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d block;  lo: Y + 40 + same.  group 0: p_j.r, group 1: p_i.r, d
         {
-            float prj[32], pri[32];
+            const float *src = grp == 0 ? sJ : sI;
+            float pr[32];
 #pragma unroll
             for (int s = 0; s < S; s += 4) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(sJ + 32 + s));
-                const float4 y = __ldg(reinterpret_cast<const float4 *>(sJ + 64 + s));
-                const float4 z = __ldg(reinterpret_cast<const float4 *>(sJ + 96 + s));
-                prj[s + 0] = fmaf(g.z, z.x, fmaf(g.y, y.x, g.x * x.x));
-                prj[s + 1] = fmaf(g.z, z.y, fmaf(g.y, y.y, g.x * x.y));
-                prj[s + 2] = fmaf(g.z, z.z, fmaf(g.y, y.z, g.x * x.z));
-                prj[s + 3] = fmaf(g.z, z.w, fmaf(g.y, y.w, g.x * x.w));
-                const float4 xi = __ldg(reinterpret_cast<const float4 *>(sI + 32 + s));
-                const float4 yi = __ldg(reinterpret_cast<const float4 *>(sI + 64 + s));
-                const float4 zi = __ldg(reinterpret_cast<const float4 *>(sI + 96 + s));
-                pri[s + 0] = fmaf(g.z, zi.x, fmaf(g.y, yi.x, g.x * xi.x));
-                pri[s + 1] = fmaf(g.z, zi.y, fmaf(g.y, yi.y, g.x * xi.y));
-                pri[s + 2] = fmaf(g.z, zi.z, fmaf(g.y, yi.z, g.x * xi.z));
-                pri[s + 3] = fmaf(g.z, zi.w, fmaf(g.y, yi.w, g.x * xi.w));
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(src + 32 + s));
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(src + 64 + s));
+                const float4 z = __ldg(reinterpret_cast<const float4 *>(src + 96 + s));
+                pr[s + 0] = fmaf(g.z, z.x, fmaf(g.y, y.x, g.x * x.x));
+                pr[s + 1] = fmaf(g.z, z.y, fmaf(g.y, y.y, g.x * x.y));
+                pr[s + 2] = fmaf(g.z, z.z, fmaf(g.y, y.z, g.x * x.z));
+                pr[s + 3] = fmaf(g.z, z.w, fmaf(g.y, y.w, g.x * x.w));
             }
-            uint32_t hj[16], lj[16], hi_[16], li_[16], hd[8], ld[8];
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-                if (SPLIT) {
-                    tc::split_bf16x2(prj[2 * u], prj[2 * u + 1], hj[u], lj[u]);
-                    tc::split_bf16x2(pri[2 * u], pri[2 * u + 1], hi_[u], li_[u]);
-                } else {
-                    hj[u] = tc::pack_bf16x2(prj[2 * u], prj[2 * u + 1]);
-                    hi_[u] = tc::pack_bf16x2(pri[2 * u], pri[2 * u + 1]);
-                }
+                if (SPLIT) tc::split_bf16x2(pr[2 * u], pr[2 * u + 1], hi[u], lo[u]);
+                else hi[u] = tc::pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
             }
+            tc::tmem_st16(tlane + TY + 16 * grp, hi);
+            if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16 * grp, lo);
+            if (grp == 1) {
+                uint32_t hd[8], ld[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) hd[u] = ld[u] = 0u;
-            if (SPLIT) tc::split_bf16x2(g.w, 0.f, hd[0], ld[0]); else hd[0] = tc::pack_bf16x2(g.w, 0.f);
-            // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d block;  lo: Y + 40 + same
-            tc::tmem_st16(tlane + TY + 0, hj);
-            tc::tmem_st16(tlane + TY + 16, hi_);
-            tc::tmem_st8(tlane + TY + 32, hd);
-            if (SPLIT) {
-                tc::tmem_st16(tlane + TY + 40, lj);
-                tc::tmem_st16(tlane + TY + 56, li_);
-                tc::tmem_st8(tlane + TY + 72, ld);
+                for (int u = 0; u < 8; ++u) hd[u] = ld[u] = 0u;
+                if (SPLIT) tc::split_bf16x2(g.w, 0.f, hd[0], ld[0]); else hd[0] = tc::pack_bf16x2(g.w, 0.f);
+                tc::tmem_st8(tlane + TY + 32, hd);
+                if (SPLIT) tc::tmem_st8(tlane + TY + 72, ld);
             }
         }
         tc::wait_st();
@@ -296,21 +291,35 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             }
             tc::umma_commit(bar);
         }
+        // prefetch the per-atom factors of this thread's first E1 chunk while the tensor core works
+        float4 pu[8], pt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            pu[u] = __ldg(reinterpret_cast<const float4 *>(cI + 64 * grp + 4 * u));
+            pt[u] = __ldg(reinterpret_cast<const float4 *>(tJ + 64 * grp + 4 * u));
+        }
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
         tc::fence_after_sync();
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + U_i + T_j) -> A2 (X, in place)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * grp + cc;
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX + 32 * c, r);
             float x[32];
 #pragma unroll
-            for (int u = 0; u < 32; u += 4) {
-                const float4 uu = __ldg(reinterpret_cast<const float4 *>(cI + 32 * c + u));
-                const float4 tt = __ldg(reinterpret_cast<const float4 *>(tJ + 32 * c + u));
-                x[u + 0] = uu.x + tt.x; x[u + 1] = uu.y + tt.y; x[u + 2] = uu.z + tt.z; x[u + 3] = uu.w + tt.w;
+            for (int u = 0; u < 8; ++u) {
+                x[4 * u + 0] = pu[u].x + pt[u].x; x[4 * u + 1] = pu[u].y + pt[u].y;
+                x[4 * u + 2] = pu[u].z + pt[u].z; x[4 * u + 3] = pu[u].w + pt[u].w;
+            }
+            if (cc == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    pu[u] = __ldg(reinterpret_cast<const float4 *>(cI + 32 * (c + 1) + 4 * u));
+                    pt[u] = __ldg(reinterpret_cast<const float4 *>(tJ + 32 * (c + 1) + 4 * u));
+                }
             }
             tc::wait_ld();
 #pragma unroll
@@ -333,7 +342,8 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
 
         // ---------------------------------------------------------------- E2: h2 = ELU(D2 + b2) -> A3 (Y, in place)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * grp + cc;
             uint32_t r[32];
             tc::tmem_ld32(tlane + TY + 32 * c, r);
             tc::wait_ld();
@@ -358,22 +368,25 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             issue_gemm<SPLIT>(tbase, TX + 32, TY + 64, 16, 4, img_hi + tcimg::B3V, img_lo + tcimg::B3V, 64);
             tc::umma_commit(bar);
         }
-        if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 3);
-        phase ^= 1u;
-        tc::fence_after_sync();
-
-        // ---------------------------------------------------------------- E3: attention
-        float wq[NH], wp0[NH], wp1s[NH], wp2[NH];
+        // queries of the centre atom while the tensor core works: [t][h][k] = t*6 + h*3 + k, pre-divided by sdk
+        float qv[12];
         {
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TX, r);                               // [0,3) Kq, [16,25) Kp
-            const float *Qi = cI + NODE_C_Q;                             // [t][h][k] = t*6 + h*3 + k, pre-divided by sdk
-            float qv[12];
+            const float *Qi = cI + NODE_C_Q;
 #pragma unroll
             for (int u = 0; u < 12; u += 4) {
                 const float4 q4 = __ldg(reinterpret_cast<const float4 *>(Qi + u));
                 qv[u] = q4.x; qv[u + 1] = q4.y; qv[u + 2] = q4.z; qv[u + 3] = q4.w;
             }
+        }
+        if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 3);
+        phase ^= 1u;
+        tc::fence_after_sync();
+
+        // ---------------------------------------------------------------- E3: attention (both groups compute the weights)
+        float wq[NH], wp0[NH], wp1s[NH], wp2[NH];
+        {
+            uint32_t r[32];
+            tc::tmem_ld32(tlane + TX, r);                               // [0,3) Kq, [16,25) Kp
             tc::wait_ld();
             float kq[3], kp[9];
 #pragma unroll
@@ -395,10 +408,10 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             mx[2] = seg_max_tc<SEG>(fmaxf(lp[0][0], fmaxf(lp[0][1], lp[0][2])));
             mx[3] = seg_max_tc<SEG>(fmaxf(lp[1][0], fmaxf(lp[1][1], lp[1][2])));
             if (WPA == 2) {
-                if (lane == 0) { red[warp * 8 + 0] = mx[0]; red[warp * 8 + 1] = mx[1]; red[warp * 8 + 2] = mx[2]; red[warp * 8 + 3] = mx[3]; }
+                if (lane == 0) { redg[quarter * 8 + 0] = mx[0]; redg[quarter * 8 + 1] = mx[1]; redg[quarter * 8 + 2] = mx[2]; redg[quarter * 8 + 3] = mx[3]; }
                 __syncthreads();
 #pragma unroll
-                for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], red[(warp ^ 1) * 8 + u]);
+                for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], redg[(quarter ^ 1) * 8 + u]);
             }
             float eq[NH], ep[NH][3], sm[4];
 #pragma unroll
@@ -412,10 +425,10 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             sm[2] = seg_sum_tc<SEG>(ep[0][0] + ep[0][1] + ep[0][2]);
             sm[3] = seg_sum_tc<SEG>(ep[1][0] + ep[1][1] + ep[1][2]);
             if (WPA == 2) {
-                if (lane == 0) { red[warp * 8 + 4] = sm[0]; red[warp * 8 + 5] = sm[1]; red[warp * 8 + 6] = sm[2]; red[warp * 8 + 7] = sm[3]; }
+                if (lane == 0) { redg[quarter * 8 + 4] = sm[0]; redg[quarter * 8 + 5] = sm[1]; redg[quarter * 8 + 6] = sm[2]; redg[quarter * 8 + 7] = sm[3]; }
                 __syncthreads();
 #pragma unroll
-                for (int u = 0; u < 4; ++u) sm[u] += red[(warp ^ 1) * 8 + 4 + u];
+                for (int u = 0; u < 4; ++u) sm[u] += redg[(quarter ^ 1) * 8 + 4 + u];
             }
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
@@ -426,20 +439,18 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
                 wp2[h] = ep[h][2] * ip;                // Mp[h, token p_j]
             }
         }
-        // weighted sums, reduced over the atom's edges; lane keeps EPL elements per 32-vector
-        float *zw = Zs + (warp * APW + (lane / SEG)) * 256 + (lane % SEG) * EPL;
-        {
+        // weighted sums, reduced over the atom's edges; lane keeps EPL elements per 32-vector.
+        // group 0: Zq (2 vectors) + Zp[c=0] (2 vectors); group 1: Zp[c=1], Zp[c=2] (4 vectors)
+        float *zw = Zs + (quarter * APW + (lane / SEG)) * 256 + (lane % SEG) * EPL;
+        if (grp == 0) {
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX + 32, r);                          // V0
             tc::wait_ld();
-            float v0[32];
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v0[u] = __uint_as_float(r[u]) + b3[32 + u];
 #pragma unroll
             for (int h = 0; h < NH; ++h) {                              // Zq = Mq . V0   (src/model_operations.py:143)
                 float v[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) v[u] = wq[h] * v0[u];
+                for (int u = 0; u < 32; ++u) v[u] = wq[h] * (__uint_as_float(r[u]) + b3[32 + u]);
                 transpose_reduce<SEG>(v, lane);
 #pragma unroll
                 for (int t = 0; t < EPL; ++t) zw[h * 32 + t] = v[t];
@@ -455,6 +466,7 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             const float gr[3] = {g.x, g.y, g.z};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {                               // Zp = Mp . [V1 (x) r ; p_i ; p_j]   (:131-136, :144)
+                if ((c == 0) != (grp == 0)) continue;                   // warp-uniform
                 float pj[32];
 #pragma unroll
                 for (int u = 0; u < 32; u += 4) {
@@ -479,39 +491,42 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
         __syncthreads();
 
-        // ---------------------------------------------------------------- per-atom projections, warp = atom
-        for (int a = warp; a < TA; a += TC_THREADS / 32) {
+        // ---------------------------------------------------------------- per-atom projections
+        // work unit = (atom, part): part 0 = qpm MLP on Zq, parts 1..3 = ppm on Zp[c]; 8 warps share TA*4 units
+        for (int unit = warp; unit < TA * 4; unit += TC_THREADS / 32) {
+            const int a = unit >> 2, part = unit & 3;
             const int ia = tile * TA + a;
-            if (ia >= n_atoms) break;
-            // partial sums of atom a: warps a*WPA .. a*WPA+WPA-1 (nn = 64), else slot a % APW of warp a / APW
-            const float *z0 = WPA == 2 ? Zs + (a * 2) * 256 : Zs + ((a / APW) * APW + (a % APW)) * 256;
-            const float *z1 = z0 + 256;
-            const float *si = state_in + (size_t)(ia + 1) * SR;
-            float h = __ldg(lw + L::O_Q1B + lane);             // qpm (src/model_operations.py:147)
-            float p0 = 0.f, p1 = 0.f, p2 = 0.f;                // ppm (:148)
+            if (ia >= n_atoms) continue;
+            const float *z0 = Zs + (WPA == 2 ? a * 2 : a) * 256 + part * 64;
+            const float *si = state_in + (size_t)(ia + 1) * SR + part * 32;
+            float *so = state_out + (size_t)(ia + 1) * SR + part * 32;
+            if (part == 0) {                                   // qpm (src/model_operations.py:147)
+                float h = __ldg(lw + L::O_Q1B + lane);
 #pragma unroll 8
-            for (int kk = 0; kk < 64; ++kk) {
-                float zq = z0[kk], za = z0[64 + kk], zb = z0[128 + kk], zc = z0[192 + kk];
-                if (WPA == 2) { zq += z1[kk]; za += z1[64 + kk]; zb += z1[128 + kk]; zc += z1[192 + kk]; }
-                h = fmaf(zq, __ldg(lw + L::O_Q1 + kk * 32 + lane), h);
-                const float wp = __ldg(lw + L::O_P + kk * 32 + lane);
-                p0 = fmaf(za, wp, p0);
-                p1 = fmaf(zb, wp, p1);
-                p2 = fmaf(zc, wp, p2);
+                for (int kk = 0; kk < 64; ++kk) {
+                    float zq = z0[kk];
+                    if (WPA == 2) zq += z0[256 + kk];
+                    h = fmaf(zq, __ldg(lw + L::O_Q1 + kk * 32 + lane), h);
+                }
+                h = elu(h);
+                float g2 = __ldg(lw + L::O_Q2B + lane);
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) g2 = fmaf(__shfl_sync(FULLM, h, kk), __ldg(lw + L::O_Q2 + kk * 32 + lane), g2);
+                g2 = elu(g2);
+                float o = __ldg(lw + L::O_Q3B + lane);
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) o = fmaf(__shfl_sync(FULLM, g2, kk), __ldg(lw + L::O_Q3 + kk * 32 + lane), o);
+                so[lane] = __ldg(si + lane) + o;               // residual (:151)
+            } else {                                           // ppm (:148), one Cartesian component
+                float p0 = 0.f;
+#pragma unroll 8
+                for (int kk = 0; kk < 64; ++kk) {
+                    float za = z0[kk];
+                    if (WPA == 2) za += z0[256 + kk];
+                    p0 = fmaf(za, __ldg(lw + L::O_P + kk * 32 + lane), p0);
+                }
+                so[lane] = __ldg(si + lane) + p0;              // residual (:152)
             }
-            h = elu(h);
-            float g2 = __ldg(lw + L::O_Q2B + lane);
-#pragma unroll
-            for (int kk = 0; kk < 32; ++kk) g2 = fmaf(__shfl_sync(FULLM, h, kk), __ldg(lw + L::O_Q2 + kk * 32 + lane), g2);
-            g2 = elu(g2);
-            float o = __ldg(lw + L::O_Q3B + lane);
-#pragma unroll
-            for (int kk = 0; kk < 32; ++kk) o = fmaf(__shfl_sync(FULLM, g2, kk), __ldg(lw + L::O_Q3 + kk * 32 + lane), o);
-            float *so = state_out + (size_t)(ia + 1) * SR;
-            so[lane] = __ldg(si + lane) + o;                   // residual (:151-152)
-            so[32 + lane] = __ldg(si + 32 + lane) + p0;
-            so[64 + lane] = __ldg(si + 64 + lane) + p1;
-            so[96 + lane] = __ldg(si + 96 + lane) + p2;
         }
         __syncthreads();
         tc::fence_after_sync();
@@ -524,7 +539,7 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
 template <int NN>
 constexpr size_t tc_smem_bytes() {
     constexpr int SEG = NN < 32 ? NN : 32;
-    return (size_t)tcimg::TOTAL + (size_t)(4 * (32 / SEG) * 256 + 32) * sizeof(float) + 32;
+    return (size_t)tcimg::TOTAL + (size_t)(4 * (32 / SEG) * 256 + 64) * sizeof(float) + 32;
 }
 
 template <int NN, bool SPLIT>
@@ -539,7 +554,7 @@ int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t 
         PESTO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         configured = 1;
     }
-    constexpr int TA = TC_THREADS / NN;
+    constexpr int TA = 128 / NN;
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
     edge_kernel_tc<NN, SPLIT><<<grid, TC_THREADS, smem, st>>>(lw, (const unsigned char *)tcw, n_atoms, ids32,
