@@ -203,7 +203,7 @@ def main():
     Xd, q0d, ridd = Xh.to(dev), q0h.to(dev), ridh.to(dev)
     ids1 = batch_topology(Xd, sizes, 64)
     lib = _lib.load()
-    launches_fwd = lib.pesto_forward_launch_count(model._handle(local_rank), 0)
+    launches_fwd = lib.pesto_forward_launch_count(model._handle(local_rank), 0, _lib.MODES[args.mode])
 
     def step_resident():
         return model(Xd, ids1, q0d, ridd, n_res=n_res)

@@ -102,7 +102,9 @@ int pesto_prologue(const pesto_model_t *m, const float *X, const int64_t *ids1, 
                    void *scratch8, void *stream);
 
 /* one StateUpdateLayer -- src/model_operations.py:225-242 (gathers, StateUpdate.forward :87-154, sink reset).
- * node_scratch: pesto_node_scratch_bytes(n_atoms) bytes.  state_in and state_out must not alias. */
+ * node_scratch: pesto_node_scratch_bytes(n_atoms) bytes (per-atom factors + attention sums of the layer).
+ * state_in and state_out must not alias.  Tensor-core modes use three launches here (per-atom head, fused edge
+ * kernel, per-atom tail); pesto_forward merges the tail of layer l with the head of layer l+1. */
 size_t pesto_node_scratch_bytes(int n_atoms);
 int    pesto_state_update(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32,
                           const float *geom, const float *state_in, float *state_out,
@@ -146,7 +148,7 @@ int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int 
                            int lbo, int sbo, int idesc, void *stream);
 
 /* number of kernels one pesto_forward / pesto_knn call launches (for bench.py's gpu_launches) */
-int pesto_forward_launch_count(const pesto_model_t *m, int dense_m);
+int pesto_forward_launch_count(const pesto_model_t *m, int dense_m, int mode);
 int pesto_knn_launch_count(void);
 
 #ifdef __cplusplus

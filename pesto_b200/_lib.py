@@ -37,7 +37,7 @@ SIGNATURES = {
     "pesto_unpack_state": (_i, [_vp, _i, _vp, _vp, _vp]),
     "pesto_forward_workspace_bytes": (_sz, [_i, _i]),
     "pesto_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _i, _vp]),
-    "pesto_forward_launch_count": (_i, [_vp, _i]),
+    "pesto_forward_launch_count": (_i, [_vp, _i, _i]),
     "pesto_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

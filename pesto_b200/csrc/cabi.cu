@@ -27,12 +27,6 @@ int check_cuda(cudaError_t e, const char *what) {
     return PESTO_ECUDA;
 }
 
-int launch_state_update_tc(const float *layer_w, const void *layer_tc, int nn, int n_atoms, const int32_t *ids32,
-                           const float *geom, const float *state_in, float *state_out, float *node_scratch, int mode,
-                           cudaStream_t st, cudaEvent_t *ev);
-size_t tc_layer_bytes();
-void pack_tc_layer(const float *layer_blob_host, void *dst_host);
-
 }  // namespace pesto
 
 using namespace pesto;
@@ -193,7 +187,7 @@ Workspace carve_workspace(void *base, int n_atoms, int n_res) {
     w.state_b = (float *)take(rows * SR * sizeof(float));
     w.ids32 = (int32_t *)take((size_t)n_atoms * KMAX * sizeof(int32_t));
     w.geom = (float *)take((size_t)n_atoms * KMAX * 4 * sizeof(float));
-    w.node = (float *)take(rows * (NODE_T_STRIDE + NODE_C_STRIDE) * sizeof(float));
+    w.node = (float *)take(rows * (NODE_T_STRIDE + NODE_C_STRIDE + 256) * sizeof(float));
     w.rid = (int32_t *)take((size_t)n_atoms * sizeof(int32_t));
     w.status = (int32_t *)take(4 * sizeof(int32_t));
     w.pool = take(pool_scratch_bytes(n_atoms, n_res));
@@ -314,8 +308,8 @@ int pesto_prologue(const pesto_model_t *m, const float *X, const int64_t *ids1, 
                            (cudaStream_t)stream);
 }
 
-size_t pesto_node_scratch_bytes(int n_atoms) {
-    return ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE) * sizeof(float);
+size_t pesto_node_scratch_bytes(int n_atoms) {   // per-atom factors T | C and the attention sums Z of one layer
+    return ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE + 256) * sizeof(float);
 }
 
 static int state_update_impl(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
@@ -332,7 +326,9 @@ static int state_update_impl(const pesto_model_t *m, int layer, int n_atoms, con
                                         (float *)node_scratch, (cudaStream_t)stream, ev);
     if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16)
         return launch_state_update_tc(m->layer(layer), m->layer_tc(layer), m->nn[layer], n_atoms, ids32, geom, state_in,
-                                      state_out, (float *)node_scratch, mode, (cudaStream_t)stream, ev);
+                                      state_out, (float *)node_scratch,
+                                      (float *)node_scratch + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE), mode,
+                                      (cudaStream_t)stream, ev);
     set_error("pesto_state_update: unknown mode %d", mode);
     return PESTO_EINVAL;
 }
@@ -421,10 +417,27 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
     int rc = launch_prologue(m->head(), m->q0_dim, X, ids1, ids_cols, q0, n_atoms, w.state_a, w.ids32, w.geom, w.status, st);
     if (rc != PESTO_OK) return rc;
     float *cur = w.state_a, *nxt = w.state_b;
-    for (int l = 0; l < m->n_layers; ++l) {
-        rc = pesto_state_update(m, l, n_atoms, w.ids32, w.geom, cur, nxt, w.node, mode, stream);
+    if (mode == PESTO_MODE_FP32) {
+        for (int l = 0; l < m->n_layers; ++l) {
+            rc = pesto_state_update(m, l, n_atoms, w.ids32, w.geom, cur, nxt, w.node, mode, stream);
+            if (rc != PESTO_OK) return rc;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+    } else if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16) {
+        // tensor-core path: the per-atom tail of layer l and the per-atom head of layer l+1 share one launch
+        float *Z = w.node + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE);
+        rc = launch_node_fused(nullptr, m->layer(0), cur, nullptr, nullptr, n_atoms, w.node, st);
         if (rc != PESTO_OK) return rc;
-        float *t = cur; cur = nxt; nxt = t;
+        for (int l = 0; l < m->n_layers; ++l) {
+            rc = launch_edge_tc_layer(m->layer(l), m->layer_tc(l), m->nn[l], n_atoms, w.ids32, w.geom, cur, w.node, Z, mode, st);
+            if (rc != PESTO_OK) return rc;
+            rc = launch_node_fused(m->layer(l), l + 1 < m->n_layers ? m->layer(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, st);
+            if (rc != PESTO_OK) return rc;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+    } else {
+        set_error("pesto_forward: unknown mode %d", mode);
+        return PESTO_EINVAL;
     }
     const int32_t *rid_dev = rid;
     if (M) {
@@ -438,9 +451,9 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
     return launch_pool_decode(m->head(), cur, rid_dev, n_atoms, n_res, z, w.pool, w.status + 1, st);
 }
 
-int pesto_forward_launch_count(const pesto_model_t *m, int dense_m) {
+int pesto_forward_launch_count(const pesto_model_t *m, int dense_m, int mode) {
     if (!m) return 0;
-    return 3 + 2 * m->n_layers + (dense_m ? 1 : 0) + 5;
+    return 3 + 2 * m->n_layers + (mode == PESTO_MODE_FP32 ? 0 : 1) + (dense_m ? 1 : 0) + 5;
 }
 
 }  // extern "C"

@@ -124,6 +124,15 @@ int launch_state_update_fp32(const float *layer_w, int nn, int n_atoms, const in
                              const float *state_in, float *state_out, float *node_scratch, cudaStream_t st,
                              cudaEvent_t *ev = nullptr);
 int launch_node(const float *layer_w, int n_atoms, const float *state_in, float *node_scratch, cudaStream_t st);
+int launch_node_fused(const float *lw_prev, const float *lw_next, const float *state_prev, const float *Z,
+                      float *state_new, int n_atoms, float *node_scratch, cudaStream_t st);
+int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
+                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st);
+int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
+                           const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
+                           cudaStream_t st, cudaEvent_t *ev);
+size_t tc_layer_bytes();
+void pack_tc_layer(const float *layer_blob_host, void *dst_host);
 int launch_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, cudaStream_t st);
 int launch_pool_decode(const float *head_w, const float *state, const int32_t *rid, int n_atoms, int n_res,
                        float *z, void *scratch, const int32_t *poison, cudaStream_t st);

@@ -192,7 +192,7 @@ template <int NN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ tcw, int n_atoms,
                const int32_t *__restrict__ ids32, const float4 *__restrict__ geom, const float *__restrict__ state_in,
-               const float *__restrict__ nodeT, const float *__restrict__ nodeC, float *__restrict__ state_out) {
+               const float *__restrict__ nodeT, const float *__restrict__ nodeC, float *__restrict__ Zout) {
     constexpr int TA = 128 / NN;                    // atoms per tile
     constexpr int SEG = NN < 32 ? NN : 32;          // lanes of one atom inside a warp
     constexpr int APW = 32 / SEG;                   // atoms per warp
@@ -204,7 +204,8 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
     const float *b3 = b2 + 128;
     float *Zs = reinterpret_cast<float *>(img + tcimg::TOTAL);          // [4 lane quarters][APW][256]
     float *red = Zs + 4 * APW * 256;                                    // [2 groups][4][8]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 64);
+    float *Ws = red + 64;                                               // [128 edges][4]: Mp[h, token p_j] (2), row j, pad
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Ws + 128 * 4);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -216,7 +217,6 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
     }
     for (int u = tid; u < tcimg::TOTAL / 16; u += TC_THREADS)
         reinterpret_cast<uint4 *>(img)[u] = __ldg(reinterpret_cast<const uint4 *>(tcw) + u);
-    if (blockIdx.x == 0 && tid < SR) state_out[tid] = 0.f;   // sink row stays zero (src/model_operations.py:239-240)
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -229,12 +229,19 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
     float *redg = red + grp * 32;
 
     const int n_tiles = (n_atoms + TA - 1) / TA;
+    const int e = tid & 127;                                       // edge slot inside the tile = TMEM lane
+    const int a_loc = e / NN, k = e % NN;
+    int j_next = 0;
+    float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)blockIdx.x < n_tiles) {
+        const int i0 = min((int)blockIdx.x * TA + a_loc, n_atoms - 1);
+        j_next = ids32[(size_t)i0 * KMAX + k];
+        g_next = geom[(size_t)i0 * KMAX + k];
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int e = tid & 127;                                   // edge slot inside the tile = TMEM lane
-        const int a_loc = e / NN, k = e % NN;
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
-        const int j = ids32[(size_t)i * KMAX + k];
-        const float4 g = geom[(size_t)i * KMAX + k];
+        const int j = j_next;
+        const float4 g = g_next;
         const float *sI = state_in + (size_t)(i + 1) * SR;
         const float *sJ = state_in + (size_t)j * SR;
         const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
@@ -383,7 +390,7 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         tc::fence_after_sync();
 
         // ---------------------------------------------------------------- E3: attention (both groups compute the weights)
-        float wq[NH], wp0[NH], wp1s[NH], wp2[NH];
+        float wq[NH], wp0[NH], wp1s[NH];
         {
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX, r);                               // [0,3) Kq, [16,25) Kp
@@ -436,8 +443,9 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
                 wq[h] = eq[h] * iq;                    // Mq[h]
                 wp0[h] = ep[h][0] * ip;                // Mp[h, token V1 (x) r]
                 wp1s[h] = seg_sum_tc<SEG>(ep[h][1] * ip);   // sum over this warp's edges of Mp[h, token p_i]
-                wp2[h] = ep[h][2] * ip;                // Mp[h, token p_j]
             }
+            if (grp == 0)                              // the p_j token is summed warp-per-atom below (coalesced rows)
+                *reinterpret_cast<float4 *>(Ws + 4 * e) = make_float4(ep[0][2] / sm[2], ep[1][2] / sm[3], __int_as_float(j), 0.f);
         }
         // weighted sums, reduced over the atom's edges; lane keeps EPL elements per 32-vector.
         // group 0: Zq (2 vectors) + Zp[c=0] (2 vectors); group 1: Zp[c=1], Zp[c=2] (4 vectors)
@@ -467,18 +475,12 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
 #pragma unroll
             for (int c = 0; c < 3; ++c) {                               // Zp = Mp . [V1 (x) r ; p_i ; p_j]   (:131-136, :144)
                 if ((c == 0) != (grp == 0)) continue;                   // warp-uniform
-                float pj[32];
-#pragma unroll
-                for (int u = 0; u < 32; u += 4) {
-                    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(sJ + 32 + 32 * c + u));
-                    pj[u] = p4.x; pj[u + 1] = p4.y; pj[u + 2] = p4.z; pj[u + 3] = p4.w;
-                }
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
                     float v[32];
                     const float a0 = wp0[h] * gr[c];
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) v[u] = fmaf(a0, v1[u], wp2[h] * pj[u]);
+                    for (int u = 0; u < 32; ++u) v[u] = a0 * v1[u];
                     transpose_reduce<SEG>(v, lane);
 #pragma unroll
                     for (int t = 0; t < EPL; ++t) {
@@ -488,45 +490,47 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
                 }
             }
         }
+        if (tile + (int)gridDim.x < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
+            const int in = min((tile + (int)gridDim.x) * TA + a_loc, n_atoms - 1);
+            j_next = ids32[(size_t)in * KMAX + k];
+            g_next = geom[(size_t)in * KMAX + k];
+        }
         tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
         __syncthreads();
 
-        // ---------------------------------------------------------------- per-atom projections
-        // work unit = (atom, part): part 0 = qpm MLP on Zq, parts 1..3 = ppm on Zp[c]; 8 warps share TA*4 units
+        // ---------------------------------------------------------------- attention sums Z -> global
+        // work unit = (atom, part): part 0 = Zq (64 values), parts 1..3 = Zp[c] incl. the p_j token, summed here with
+        // lane = channel and one coalesced 128 B row per edge.  The per-atom projections qpm / ppm run in the next
+        // node kernel, where their weights are reused across 8 atoms.
         for (int unit = warp; unit < TA * 4; unit += TC_THREADS / 32) {
             const int a = unit >> 2, part = unit & 3;
             const int ia = tile * TA + a;
             if (ia >= n_atoms) continue;
             const float *z0 = Zs + (WPA == 2 ? a * 2 : a) * 256 + part * 64;
-            const float *si = state_in + (size_t)(ia + 1) * SR + part * 32;
-            float *so = state_out + (size_t)(ia + 1) * SR + part * 32;
-            if (part == 0) {                                   // qpm (src/model_operations.py:147)
-                float h = __ldg(lw + L::O_Q1B + lane);
-#pragma unroll 8
-                for (int kk = 0; kk < 64; ++kk) {
-                    float zq = z0[kk];
-                    if (WPA == 2) zq += z0[256 + kk];
-                    h = fmaf(zq, __ldg(lw + L::O_Q1 + kk * 32 + lane), h);
-                }
-                h = elu(h);
-                float g2 = __ldg(lw + L::O_Q2B + lane);
+            float zq0 = z0[lane], zq1 = z0[32 + lane];
+            if (WPA == 2) { zq0 += z0[256 + lane]; zq1 += z0[256 + 32 + lane]; }
+            if (part > 0) {
+                const float *ws = Ws + 4 * (a * NN);
+                constexpr int PB = NN < 16 ? NN : 16;          // independent row loads in flight per batch
+#pragma unroll 1
+                for (int e0 = 0; e0 < NN; e0 += PB) {
+                    float4 w4[PB];
+                    float pj[PB];
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) g2 = fmaf(__shfl_sync(FULLM, h, kk), __ldg(lw + L::O_Q2 + kk * 32 + lane), g2);
-                g2 = elu(g2);
-                float o = __ldg(lw + L::O_Q3B + lane);
+                    for (int u = 0; u < PB; ++u) w4[u] = *reinterpret_cast<const float4 *>(ws + 4 * (e0 + u));
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) o = fmaf(__shfl_sync(FULLM, g2, kk), __ldg(lw + L::O_Q3 + kk * 32 + lane), o);
-                so[lane] = __ldg(si + lane) + o;               // residual (:151)
-            } else {                                           // ppm (:148), one Cartesian component
-                float p0 = 0.f;
-#pragma unroll 8
-                for (int kk = 0; kk < 64; ++kk) {
-                    float za = z0[kk];
-                    if (WPA == 2) za += z0[256 + kk];
-                    p0 = fmaf(za, __ldg(lw + L::O_P + kk * 32 + lane), p0);
+                    for (int u = 0; u < PB; ++u)
+                        pj[u] = __ldg(state_in + (size_t)__float_as_int(w4[u].z) * SR + part * 32 + lane);
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) {
+                        zq0 = fmaf(w4[u].x, pj[u], zq0);
+                        zq1 = fmaf(w4[u].y, pj[u], zq1);
+                    }
                 }
-                so[lane] = __ldg(si + lane) + p0;              // residual (:152)
             }
+            float *zo = Zout + (size_t)(ia + 1) * 256 + part * 64;
+            zo[lane] = zq0;
+            zo[32 + lane] = zq1;
         }
         __syncthreads();
         tc::fence_after_sync();
@@ -539,12 +543,12 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
 template <int NN>
 constexpr size_t tc_smem_bytes() {
     constexpr int SEG = NN < 32 ? NN : 32;
-    return (size_t)tcimg::TOTAL + (size_t)(4 * (32 / SEG) * 256 + 64) * sizeof(float) + 32;
+    return (size_t)tcimg::TOTAL + (size_t)(4 * (32 / SEG) * 256 + 64 + 128 * 4) * sizeof(float) + 32;
 }
 
 template <int NN, bool SPLIT>
 int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom,
-                   const float *state_in, const float *nodeT, const float *nodeC, float *state_out, cudaStream_t st) {
+                   const float *state_in, const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
     static int configured = 0, n_sm = 0;
     constexpr size_t smem = tc_smem_bytes<NN>();
     if (!configured) {
@@ -558,7 +562,7 @@ int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t 
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
     edge_kernel_tc<NN, SPLIT><<<grid, TC_THREADS, smem, st>>>(lw, (const unsigned char *)tcw, n_atoms, ids32,
-                                                            (const float4 *)geom, state_in, nodeT, nodeC, state_out);
+                                                            (const float4 *)geom, state_in, nodeT, nodeC, Zout);
     PESTO_CUDA(cudaGetLastError());
     if (getenv("PESTO_TC_DEBUG")) {       // debugging aid: synchronise and report a timed-out tensor-core stage
         PESTO_CUDA(cudaStreamSynchronize(st));
@@ -576,12 +580,12 @@ int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t 
 
 template <bool SPLIT>
 int dispatch_tc(int nn, const float *lw, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom,
-                const float *state_in, const float *nodeT, const float *nodeC, float *state_out, cudaStream_t st) {
+                const float *state_in, const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
     switch (nn) {
-        case 8:  return launch_edge_tc<8, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 16: return launch_edge_tc<16, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 32: return launch_edge_tc<32, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-        case 64: return launch_edge_tc<64, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
+        case 8:  return launch_edge_tc<8, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 16: return launch_edge_tc<16, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 32: return launch_edge_tc<32, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 64: return launch_edge_tc<64, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
         default:
             set_error("state_update: unsupported nn=%d (supported: 8, 16, 32, 64)", nn);
             return PESTO_EINVAL;
@@ -590,9 +594,10 @@ int dispatch_tc(int nn, const float *lw, const void *tcw, int n_atoms, const int
 
 }  // namespace
 
-int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
-                           const float *state_in, float *state_out, float *node_scratch, int mode, cudaStream_t st,
-                           cudaEvent_t *ev) {
+// Edge kernel only: attention sums of one layer -> Z[n_atoms+1][256] (row 0 unused).  nodeT / nodeC must hold the
+// layer's per-atom factors (launch_node_fused).
+int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
+                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st) {
     if (!tcw) {
         set_error("state_update: tensor-core weight images are missing");
         return PESTO_ESTATE;
@@ -600,15 +605,23 @@ int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms
     const int n_rows = n_atoms + 1;
     float *nodeT = node_scratch;
     float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
+    return mode == PESTO_MODE_BF16X3 ? dispatch_tc<true>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st)
+                                     : dispatch_tc<false>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st);
+}
+
+// One complete layer state_in -> state_out (staged API, three launches): head factors, edge kernel, per-atom tail.
+// `ev` (optional, 3 events): before the head kernel, between head and edge kernel, after the edge kernel.
+int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
+                           const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
+                           cudaStream_t st, cudaEvent_t *ev) {
     if (ev) PESTO_CUDA(cudaEventRecord(ev[0], st));
-    int rc = launch_node(lw, n_atoms, state_in, node_scratch, st);
+    int rc = launch_node_fused(nullptr, lw, state_in, nullptr, nullptr, n_atoms, node_scratch, st);
     if (rc != PESTO_OK) return rc;
     if (ev) PESTO_CUDA(cudaEventRecord(ev[1], st));
-    rc = mode == PESTO_MODE_BF16X3
-             ? dispatch_tc<true>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st)
-             : dispatch_tc<false>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, state_out, st);
-    if (rc == PESTO_OK && ev) PESTO_CUDA(cudaEventRecord(ev[2], st));
-    return rc;
+    rc = launch_edge_tc_layer(lw, tcw, nn, n_atoms, ids32, geom, state_in, node_scratch, Z, mode, st);
+    if (rc != PESTO_OK) return rc;
+    if (ev) PESTO_CUDA(cudaEventRecord(ev[2], st));
+    return launch_node_fused(lw, nullptr, state_in, Z, state_out, n_atoms, node_scratch, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------

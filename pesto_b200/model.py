@@ -66,10 +66,11 @@ class Model(torch.nn.Module):
       q0        [N, N0] float32 features
       M         [N, R] float membership (rows one-hot), as the reference; or, as an extension that avoids the dense
                 matrix, a 1-D integer tensor with the residue column of every atom (pass n_res= to skip a sync).
-    `mode`: 'fp32' (parity, FFMA), 'bf16x3' (tensor cores, split bf16) or 'bf16' (tensor cores, speed).
+    `mode`: 'bf16x3' (default: tensor cores, 3-term split bf16, logits within 1e-3 of the reference), 'fp32' (FFMA,
+    exact mode) or 'bf16' (tensor cores, single pass, speed mode with ~1e-1 logit error).
     """
 
-    def __init__(self, config, mode="fp32"):
+    def __init__(self, config, mode="bf16x3"):
         super().__init__()
         for lp in config["sum"]:
             if (lp["Ns"], lp["Nh"], lp["Nk"]) != (32, 2, 3) or lp["nn"] not in (8, 16, 32, 64):
@@ -187,4 +188,4 @@ class Model(torch.nn.Module):
         return z if out_device == dev else z.to(out_device)
 
     def launches_per_forward(self, dense_m=True):
-        return len(self.config["sum"]) * 2 + 3 + 5 + (1 if dense_m else 0)
+        return len(self.config["sum"]) * 2 + 3 + 5 + (1 if dense_m else 0) + (0 if self.mode == "fp32" else 1)

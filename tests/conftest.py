@@ -67,7 +67,7 @@ def cuda_models():
 
     def get(tag):
         if tag not in cache:
-            m = Model(load_config(tag))
+            m = Model(load_config(tag), mode="fp32")      # tests pick tensor-core modes explicitly
             sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
             m.load_state_dict(sd)
             cache[tag] = m.eval().to("cuda")
