@@ -113,7 +113,14 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr uint32_t TM_COLS = 256;     // TMEM columns per CTA: X = [0,128), Y = [128,256)
 constexpr uint32_t TX = 0, TY = 128;
 
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
+// exp via one MUFU: ex2.approx.ftz (no denormal fix-up code around it; inputs below -126 flush to 0, which is exact
+// enough for ELU's exp(x) - 1 and for softmax weights)
+__device__ __forceinline__ float exp_fast(float x) {
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 1.4426950408889634f));
+    return t;
+}
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (exp_fast(x) - 1.0f); }
 
 template <int SEG>
 __device__ __forceinline__ float seg_max_tc(float v) {
@@ -423,9 +430,9 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             float eq[NH], ep[NH][3], sm[4];
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-                eq[h] = __expf(lq[h] - mx[h]);
+                eq[h] = exp_fast(lq[h] - mx[h]);
 #pragma unroll
-                for (int gk = 0; gk < 3; ++gk) ep[h][gk] = __expf(lp[h][gk] - mx[2 + h]);
+                for (int gk = 0; gk < 3; ++gk) ep[h][gk] = exp_fast(lp[h][gk] - mx[2 + h]);
             }
             sm[0] = seg_sum_tc<SEG>(eq[0]);
             sm[1] = seg_sum_tc<SEG>(eq[1]);
