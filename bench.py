@@ -178,6 +178,8 @@ def main():
     from pesto_b200.data_encoding import batch_topology
     from pesto_b200.synth import one_hot_features
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -260,14 +260,13 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             const float *src = grp == 0 ? sJ : sI;
             float pr[32];
 #pragma unroll
-            for (int s = 0; s < S; s += 4) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(src + 32 + s));
-                const float4 y = __ldg(reinterpret_cast<const float4 *>(src + 64 + s));
-                const float4 z = __ldg(reinterpret_cast<const float4 *>(src + 96 + s));
-                pr[s + 0] = fmaf(g.z, z.x, fmaf(g.y, y.x, g.x * x.x));
-                pr[s + 1] = fmaf(g.z, z.y, fmaf(g.y, y.y, g.x * x.y));
-                pr[s + 2] = fmaf(g.z, z.z, fmaf(g.y, y.z, g.x * x.z));
-                pr[s + 3] = fmaf(g.z, z.w, fmaf(g.y, y.w, g.x * x.w));
+            for (int s = 0; s < S; s += 8) {
+                float x[8], y[8], z[8];
+                tc::ldg256(src + 32 + s, x);
+                tc::ldg256(src + 64 + s, y);
+                tc::ldg256(src + 96 + s, z);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pr[s + u] = fmaf(g.z, z[u], fmaf(g.y, y[u], g.x * x[u]));
             }
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -306,11 +305,11 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             tc::umma_commit(bar);
         }
         // prefetch the per-atom factors of this thread's first E1 chunk while the tensor core works
-        float4 pu[8], pt[8];
+        float pu[4][8], pt[4][8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            pu[u] = __ldg(reinterpret_cast<const float4 *>(cI + 64 * grp + 4 * u));
-            pt[u] = __ldg(reinterpret_cast<const float4 *>(tJ + 64 * grp + 4 * u));
+        for (int u = 0; u < 4; ++u) {
+            tc::ldg256(cI + 64 * grp + 8 * u, pu[u]);
+            tc::ldg256(tJ + 64 * grp + 8 * u, pt[u]);
         }
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
@@ -324,15 +323,14 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             tc::tmem_ld32(tlane + TX + 32 * c, r);
             float x[32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                x[4 * u + 0] = pu[u].x + pt[u].x; x[4 * u + 1] = pu[u].y + pt[u].y;
-                x[4 * u + 2] = pu[u].z + pt[u].z; x[4 * u + 3] = pu[u].w + pt[u].w;
-            }
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) x[8 * u + w] = pu[u][w] + pt[u][w];
             if (cc == 0) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    pu[u] = __ldg(reinterpret_cast<const float4 *>(cI + 32 * (c + 1) + 4 * u));
-                    pt[u] = __ldg(reinterpret_cast<const float4 *>(tJ + 32 * (c + 1) + 4 * u));
+                for (int u = 0; u < 4; ++u) {
+                    tc::ldg256(cI + 32 * (c + 1) + 8 * u, pu[u]);
+                    tc::ldg256(tJ + 32 * (c + 1) + 8 * u, pt[u]);
                 }
             }
             tc::wait_ld();

@@ -131,6 +131,13 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- 256-bit read-only global load (sm_100: LDG.E.256): one full 32-byte sector per lane ------------------------
+__device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
 // ---- bf16 splitting --------------------------------------------------------------------------------------------
 // pack two floats into bf16x2 (round to nearest even): low half = a, high half = b
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
