@@ -12,6 +12,9 @@ constexpr int NH = PESTO_NH;            // 2 heads
 constexpr int NK = PESTO_NK;            // 3
 constexpr int KMAX = PESTO_MAX_NN;      // 64
 constexpr int SR = PESTO_STATE_STRIDE;  // 128 floats per atom record
+// The tensor-core path carries edge-MLP pre-activations scaled by log2(e) so that ELU is a bare ex2 (state_update_tc.cu)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float ILOG2E = 0.6931471805599453f;
 
 // ---------------------------------------------------------------------------------------------
 // Per-layer packed weights (float offsets inside one layer block).  "T" = stored transposed,

@@ -142,8 +142,8 @@ node_fused_kernel(const float *__restrict__ lw_prev, const float *__restrict__ l
     for (int a = 0; a < NA; ++a) {
         const int r = r0 + a;
         if (r < n_rows) {
-            nodeT[(size_t)r * NODE_T_STRIDE + t] = accT[a];
-            nodeC[(size_t)r * NODE_C_STRIDE + t] = accU[a];
+            nodeT[(size_t)r * NODE_T_STRIDE + t] = LOG2E * accT[a];      // the edge kernel works in log2(e)-scaled units
+            nodeC[(size_t)r * NODE_C_STRIDE + t] = LOG2E * accU[a];
         }
     }
     // queries nqm([q, |p|]) (src/model_operations.py:119), pre-divided by sdk (:139-140); warp handles 2 atoms

@@ -1,22 +1,26 @@
 // Tensor-core (tcgen05 / TMEM) path of the StateUpdate edge kernel (src/model_operations.py:87-154).
 //
-// Tile = 128 edge slots = 128/nn atoms; one CTA of 128 threads, thread t <-> edge t <-> TMEM lane t, so every
-// MMA result row is read back by the thread that owns the edge.  Two CTAs per SM (256 TMEM columns each) overlap
-// one CTA's tensor-core wait with the other's CUDA-core stage.  Per tile:
+// Tile = 128 edge slots = 128/nn atoms.  One CTA per SM with 512 threads = two independent 256-thread tile
+// pipelines ("halves") sharing one copy of the weight images; inside a half, thread t and thread t+128 both map to
+// edge t % 128 <-> TMEM lane t % 128 and split the columns of every stage.  Per tile:
 //
-//   S0   gather p_j; A1 = [p_j.r (32) | p_i.r (32) | d, 0.. (16)] as bf16 (hi | lo) -> TMEM            (CUDA cores)
-//   M1   D1[128x128] = A1 . B1^T,  B1 = [W1 cols of p_j.r ; p_i.r ; d]                                 (tcgen05.mma)
-//   E1   h1 = ELU(D1 + U_i + T_j)  (U_i, T_j: per-atom factors from the node kernel) -> A2 in place    (CUDA cores)
+//   S0   gather p_j; A1 = [p_j.r (32) | p_i.r (32) | d, 1(atom) (16)] as bf16 (hi | lo) -> TMEM      (CUDA cores)
+//        U_i (per-atom factor) as three bf16 planes -> spare K rows of B1 in shared memory (nn >= 32)
+//   M1   D1[128x128] = A1 . B1^T,  B1 = [W1 cols of p_j.r ; p_i.r ; d ; U planes]                       (tcgen05.mma)
+//   E1   h1 = ELU(D1 + T_j)  (T_j: per-atom factor from the node kernel, gathered) -> A2 in place      (CUDA cores)
 //   M2   D2 = blockdiag(eqkm.2, epkm.2, evm.2) applied to A2's three column groups
 //   E2   h2 = ELU(D2 + b2) -> A3 in place
 //   M3   D3 = [eqkm.4 | epkm.4 | evm.4] applied to A3's column groups
-//   E3   logits, softmax over the atom's nn / 3nn tokens (warp shuffles), attention-weighted sums of V0, V1 (x) r,
-//        p_j by a recursive-halving transpose-reduce across the warp; then the per-atom qpm / ppm projections.
+//   E3   group 0: logits, softmax over the atom's nn / 3nn tokens (warp shuffles) -> attention weights in smem;
+//        group 1: V0 | V1 -> smem
+//   R    thread = (8-edge group, channel pair): attention-weighted sums of V0, V1 (x) r, p_i, p_j with packed
+//        fp32x2 FMAs, partial sums combined through shared memory -> Z[atom][256]
 //
-// The A operand of every MMA lives in TMEM (written by tcgen05.st, thread-per-row, bf16 packed two per column),
-// B (weights) in shared memory as K-major un-swizzled UMMA images prepared on the host at model-finalize time.
-// SPLIT = true computes hi*hi + lo*hi + hi*lo (3 MMAs per K step, ~2^-17 relative error: parity mode);
-// SPLIT = false is a single bf16 pass (speed mode).
+// All pre-activations are carried scaled by log2(e) (folded into B1, b2, T, U on one side and 1/log2(e) into B3
+// on the other), so ELU needs a bare ex2 and no multiply.  The A operand of every MMA lives in TMEM (written by
+// tcgen05.st, thread-per-row, bf16 packed two per column), B (weights) in shared memory as K-major un-swizzled UMMA
+// images prepared on the host at model-finalize time.  SPLIT = true computes hi*hi + lo*hi + hi*lo (3 MMAs per
+// K step, ~2^-17 relative error: parity mode); SPLIT = false is a single bf16 pass (speed mode).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -74,30 +78,30 @@ void pack_tc_layer(const float *blob, void *dst_v) {
     };
     for (int o = 0; o < 128; ++o) {
         for (int s = 0; s < 32; ++s) {
-            put(tcimg::B1, 128, o, s, blob[L::E_WB + s * 128 + o]);          // p_j . r
-            put(tcimg::B1, 128, o, 32 + s, blob[L::N_A + s * 128 + o]);      // p_i . r
+            put(tcimg::B1, 128, o, s, LOG2E * blob[L::E_WB + s * 128 + o]);          // p_j . r
+            put(tcimg::B1, 128, o, 32 + s, LOG2E * blob[L::N_A + s * 128 + o]);      // p_i . r
         }
-        put(tcimg::B1, 128, o, 64, blob[L::E_WD + o]);                       // d
+        put(tcimg::B1, 128, o, 64, LOG2E * blob[L::E_WD + o]);                       // d
     }
     for (int n = 0; n < 32; ++n)
         for (int k = 0; k < 32; ++k) {
             put(tcimg::B2Q, 32, n, k, blob[L::E_2Q + k * 32 + n]);
             put(tcimg::B2P, 32, n, k, blob[L::E_2P + k * 32 + n]);
-            if (n < 3) put(tcimg::B3Q, 16, n, k, blob[L::E_3Q + k * 4 + n]);
-            if (n < 9) put(tcimg::B3P, 16, n, k, blob[L::E_3P + k * 12 + n]);
+            if (n < 3) put(tcimg::B3Q, 16, n, k, ILOG2E * blob[L::E_3Q + k * 4 + n]);
+            if (n < 9) put(tcimg::B3P, 16, n, k, ILOG2E * blob[L::E_3P + k * 12 + n]);
         }
     for (int n = 0; n < 64; ++n)
         for (int k = 0; k < 64; ++k) {
             put(tcimg::B2V, 64, n, k, blob[L::E_2V + k * 64 + n]);
-            put(tcimg::B3V, 64, n, k, blob[L::E_3V + k * 64 + n]);
+            put(tcimg::B3V, 64, n, k, ILOG2E * blob[L::E_3V + k * 64 + n]);
         }
     float *bias = (float *)(dst + tcimg::BIAS);
     for (int i = 0; i < 32; ++i) {
-        bias[i] = blob[L::E_2QB + i];
-        bias[32 + i] = blob[L::E_2PB + i];
+        bias[i] = LOG2E * blob[L::E_2QB + i];
+        bias[32 + i] = LOG2E * blob[L::E_2PB + i];
     }
     for (int i = 0; i < 64; ++i) {
-        bias[64 + i] = blob[L::E_2VB + i];
+        bias[64 + i] = LOG2E * blob[L::E_2VB + i];
         bias[128 + 32 + i] = blob[L::E_3VB + i];
     }
     for (int i = 0; i < 3; ++i) bias[128 + i] = blob[L::E_3QB + i];
@@ -108,19 +112,93 @@ namespace {
 
 __device__ int g_tc_watchdog = 0;     // != 0: a tensor-core stage timed out (stage id), see mbar_wait
 
-constexpr int TC_THREADS = 256;     // 8 warps per tile: two column groups x four TMEM lane quarters
+constexpr int HALF_THREADS = 256;     // one tile pipeline: 8 warps = two column groups x four TMEM lane quarters
+constexpr int CTA_THREADS = 2 * HALF_THREADS;
 constexpr unsigned FULLM = 0xffffffffu;
-constexpr uint32_t TM_COLS = 256;     // TMEM columns per CTA: X = [0,128), Y = [128,256)
+constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 H, 256 H + 256): X = +0, Y = +128
 constexpr uint32_t TX = 0, TY = 128;
+constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
+constexpr int WS_STRIDE = 32;         // floats per edge row of the attention-weight buffer (128 B, chunk-swizzled)
 
-// exp via one MUFU: ex2.approx.ftz (no denormal fix-up code around it; inputs below -126 flush to 0, which is exact
-// enough for ELU's exp(x) - 1 and for softmax weights)
-__device__ __forceinline__ float exp_fast(float x) {
+// per-half shared memory (byte offsets)
+constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64..79, hi plane: W_d | per-tile U planes
+constexpr int HS_EXT_LO = HS_EXT_HI + 4096;                   // same rows, lo plane (W_d only)
+constexpr int HS_VS = HS_EXT_LO + 4096;                       // [128][VS_STRIDE] fp32; aliased by the partial sums P
+constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [128][WS_STRIDE] fp32
+constexpr int HS_RED = HS_WS + 128 * WS_STRIDE * 4;           // [4 quarters][8] softmax exchange (nn = 64)
+constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;
+constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
+constexpr int SM_HALF0 = SM_PAT + 128;
+constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // 2 mbarriers + TMEM slot
+constexpr int SM_TOTAL = SM_BAR + 32;
+static_assert(SM_HALF0 % 128 == 0 && HS_BYTES % 128 == 0, "per-half regions stay 128-byte aligned");
+
+typedef unsigned long long u64;
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 on 64-bit register pairs) -----------------------------
+__device__ __forceinline__ u64 pk2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ u64 pk2u(uint32_t a, uint32_t b) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void up2(u64 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float ex2_fast(float x) {     // one MUFU; inputs below -126 flush to 0
     float t;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
     return t;
 }
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (exp_fast(x) - 1.0f); }
+__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * LOG2E); }
+
+struct PairConsts {
+    u64 neg1, c, negc;     // (-1,-1), (log2e, log2e), (-log2e, -log2e)
+};
+
+// Activations travel scaled by c = log2(e) (folded into the weight images): with y = c x,
+//   c ELU(x) = (y - min(y,0)) + c (2^min(y,0) - 1)
+// exact for y > 0; one MUFU, one FMNMX and 1.5 packed FMA-pipe instructions per element.
+__device__ __forceinline__ u64 elu2_scaled(u64 y, const PairConsts &k) {
+    float y0, y1;
+    up2(y, y0, y1);
+    const float n0 = fminf(y0, 0.f), n1 = fminf(y1, 0.f);
+    const u64 d = fma2(pk2(n0, n1), k.neg1, y);
+    const u64 t = fma2(pk2(ex2_fast(n0), ex2_fast(n1)), k.c, k.negc);
+    return add2(d, t);
+}
+// hi = bf16x2(x), lo = bf16x2(x - hi)
+template <bool SPLIT>
+__device__ __forceinline__ void split2(u64 x, const PairConsts &k, uint32_t &hi, uint32_t &lo) {
+    float x0, x1;
+    up2(x, x0, x1);
+    hi = tc::pack_bf16x2(x0, x1);
+    if (SPLIT) {
+        const u64 l = fma2(pk2u(hi << 16, hi & 0xffff0000u), k.neg1, x);
+        float l0, l1;
+        up2(l, l0, l1);
+        lo = tc::pack_bf16x2(l0, l1);
+    }
+}
+
+__device__ __forceinline__ void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <int SEG>
 __device__ __forceinline__ float seg_max_tc(float v) {
@@ -133,43 +211,6 @@ __device__ __forceinline__ float seg_sum_tc(float v) {
 #pragma unroll
     for (int o = SEG / 2; o; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
     return v;
-}
-
-// Recursive-halving transpose-reduce: every lane holds v[0..32); afterwards lane l holds, in v[0 .. 32/SEG), the
-// sums over its SEG-lane segment of elements (l % SEG) * (32/SEG) + t.
-template <int SEG>
-__device__ __forceinline__ void transpose_reduce(float (&v)[32], int lane) {
-    int len = 32;
-#pragma unroll
-    for (int off = SEG / 2; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-        const int half = len / 2;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < half) {
-                const float send = upper ? v[i] : v[half + i];
-                const float keep = upper ? v[half + i] : v[i];
-                v[i] = keep + __shfl_xor_sync(FULLM, send, off);
-            }
-        }
-        len = half;
-    }
-}
-
-// ELU + bf16 (hi|lo) packing of 32 fp32 values -> 32 TMEM columns: [0,16) hi pairs, [16,32) lo pairs
-template <bool SPLIT>
-__device__ __forceinline__ void store_activation_chunk(uint32_t taddr, const float (&x)[32]) {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        if (SPLIT) {
-            tc::split_bf16x2(x[2 * u], x[2 * u + 1], hi[u], lo[u]);
-        } else {
-            hi[u] = tc::pack_bf16x2(x[2 * u], x[2 * u + 1]);
-        }
-    }
-    tc::tmem_st16(taddr, hi);
-    if (SPLIT) tc::tmem_st16(taddr + 16, lo);
 }
 
 // issue D[d_col .. d_col+N) (+)= A(K columns packed at a_col: hi at +8s, lo at +lo_off+8s per 16-wide K step) . B^T
@@ -191,61 +232,102 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
     }
 }
 
-// Column-split mapping: a tile (128 edges) is worked on by 8 warps.  Warps 0-3 (group 0) and warps 4-7 (group 1)
-// both map thread -> edge/TMEM lane 32*(warp%4)+lane, and each group handles half of the columns of every
-// stage.  This doubles the warps per SM (2 CTAs x 8 warps) at half the registers per thread, which is what hides
-// the gather / TMEM / shuffle latencies.
+// ELU + bf16 (hi|lo) packing of 16 packed pairs -> 32 TMEM columns: [0,16) hi pairs, [16,32) lo pairs
+template <bool SPLIT>
+__device__ __forceinline__ void activate_store(uint32_t taddr, const u64 (&y)[16], const PairConsts &k) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) split2<SPLIT>(elu2_scaled(y[u], k), k, hi[u], lo[u]);
+    tc::tmem_st16(taddr, hi);
+    if (SPLIT) tc::tmem_st16(taddr + 16, lo);
+}
+
+// One CTA per SM, 512 threads = two independent 256-thread tile pipelines ("halves") that share the weight images
+// in shared memory and interleave on the SM's four schedulers: while one half waits for the tensor core or a
+// gather, the other runs its CUDA-core stage.  Inside a half, warps 0-3 (group 0) and 4-7 (group 1) both map
+// thread -> edge / TMEM lane 32 * (warp % 4) + lane and split the columns of every stage.
 template <int NN, bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ tcw, int n_atoms,
-               const int32_t *__restrict__ ids32, const float4 *__restrict__ geom, const float *__restrict__ state_in,
-               const float *__restrict__ nodeT, const float *__restrict__ nodeC, float *__restrict__ Zout) {
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t *__restrict__ ids32,
+               const float4 *__restrict__ geom, const float *__restrict__ state_in, const float *__restrict__ nodeT,
+               const float *__restrict__ nodeC, float *__restrict__ Zout) {
     constexpr int TA = 128 / NN;                    // atoms per tile
     constexpr int SEG = NN < 32 ? NN : 32;          // lanes of one atom inside a warp
-    constexpr int APW = 32 / SEG;                   // atoms per warp
-    constexpr int EPL = 32 / SEG;                   // reduced elements per lane and 32-vector
     constexpr int WPA = NN / SEG;                   // warps (of one group) per atom: 2 for nn = 64
+    constexpr int GA = NN / 8;                      // 8-edge reduction groups per atom
+    constexpr bool UMMA = NN >= 32;                 // U_i enters through spare K columns of the first MMA
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *img = smem_raw;                                      // weight images + biases
+    unsigned char *img = smem_raw;                                      // weight images + biases (shared by both halves)
     const float *b2 = reinterpret_cast<const float *>(img + tcimg::BIAS);
     const float *b3 = b2 + 128;
-    float *Zs = reinterpret_cast<float *>(img + tcimg::TOTAL);          // [4 lane quarters][APW][256]
-    float *red = Zs + 4 * APW * 256;                                    // [2 groups][4][8]
-    float *Ws = red + 64;                                               // [128 edges][4]: Mp[h, token p_j] (2), row j, pad
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Ws + 128 * 4);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const uint32_t *pat = reinterpret_cast<const uint32_t *>(smem_raw + SM_PAT);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = warp >> 2, quarter = warp & 3;       // column group, TMEM lane quarter
-    if (warp == 0) tc::tmem_alloc(tmem_slot, TM_COLS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int H = tid >> 8, ht = tid & 255, hwarp = ht >> 5;
+    const int grp = hwarp >> 2, quarter = hwarp & 3;       // column group, TMEM lane quarter
+    unsigned char *hs = smem_raw + SM_HALF0 + H * HS_BYTES;
+    unsigned char *ext_hi = hs + HS_EXT_HI;
+    float *Vs = reinterpret_cast<float *>(hs + HS_VS);
+    float *Ws = reinterpret_cast<float *>(hs + HS_WS);
+    float *red = reinterpret_cast<float *>(hs + HS_RED);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 16);
+
+    if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
     if (tid == 0) {
-        tc::mbar_init(bar, 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR), 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 1, 1);
         tc::fence_mbar_init();
     }
-    for (int u = tid; u < tcimg::TOTAL / 16; u += TC_THREADS)
+    for (int u = tid; u < tcimg::TOTAL / 16; u += CTA_THREADS)
         reinterpret_cast<uint4 *>(img)[u] = __ldg(reinterpret_cast<const uint4 *>(tcw) + u);
+    {   // rows k = 64..79 of B1 (distance column + zeros) -> the per-half, per-tile mutable copies
+        const uint4 *src_hi = reinterpret_cast<const uint4 *>(tcw + tcimg::B1 + 8 * 2048);
+        const uint4 *src_lo = reinterpret_cast<const uint4 *>(tcw + tcimg::IMG + tcimg::B1 + 8 * 2048);
+        reinterpret_cast<uint4 *>(hs + HS_EXT_HI)[ht] = __ldg(src_hi + ht);
+        reinterpret_cast<uint4 *>(hs + HS_EXT_LO)[ht] = __ldg(src_lo + ht);
+    }
+    if (tid < 32) {      // indicator words: column k = 65 + 3 a + p (p < 3) carries plane p of U of the tile's atom a
+        const int a = tid >> 3, u = tid & 7;
+        uint32_t w = 0;
+        if (UMMA && a < TA) {
+            const int k0 = 64 + 2 * u, k1 = k0 + 1;
+            if (k0 >= 65 + 3 * a && k0 < 68 + 3 * a) w |= 0x3F80u;
+            if (k1 >= 65 + 3 * a && k1 < 68 + 3 * a) w |= 0x3F800000u;
+        }
+        reinterpret_cast<uint32_t *>(smem_raw + SM_PAT)[tid] = w;
+    }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = *tmem_slot;
+    const uint32_t tbase = *tmem_slot + (uint32_t)H * 256u;
     const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
     const uint32_t img_hi = tc::smem_u32(img), img_lo = img_hi + tcimg::IMG;
+    const uint32_t ext_hi_s = tc::smem_u32(hs + HS_EXT_HI), ext_lo_s = tc::smem_u32(hs + HS_EXT_LO);
+    const int bar_id = 1 + H, bar_g0 = 3 + H;
     uint32_t phase = 0;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
-    float *redg = red + grp * 32;
+    PairConsts kc;
+    kc.neg1 = pk2(-1.f, -1.f);
+    kc.c = pk2(LOG2E, LOG2E);
+    kc.negc = pk2(-LOG2E, -LOG2E);
 
     const int n_tiles = (n_atoms + TA - 1) / TA;
-    const int e = tid & 127;                                       // edge slot inside the tile = TMEM lane
+    const int e = ht & 127;                                        // edge slot inside the tile = TMEM lane
     const int a_loc = e / NN, k = e % NN;
+    uint32_t ind[8];                                               // this edge's indicator words (group 1 uses them)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ind[u] = UMMA ? pat[a_loc * 8 + u] : 0u;
+    const int tile0 = (int)blockIdx.x * 2 + H, tstride = (int)gridDim.x * 2;
     int j_next = 0;
     float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((int)blockIdx.x < n_tiles) {
-        const int i0 = min((int)blockIdx.x * TA + a_loc, n_atoms - 1);
+    if (tile0 < n_tiles) {
+        const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
         j_next = ids32[(size_t)i0 * KMAX + k];
         g_next = geom[(size_t)i0 * KMAX + k];
     }
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < n_tiles; tile += tstride) {
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
         const int j = j_next;
         const float4 g = g_next;
@@ -254,11 +336,13 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
         const float *tJ = nodeT + (size_t)j * NODE_T_STRIDE;
 
-        // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d] -> TMEM (Y)
-        // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d block;  lo: Y + 40 + same.  group 0: p_j.r, group 1: p_i.r, d
+        // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a)] -> TMEM (Y)
+        // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
+        // group 0: p_j.r, group 1: p_i.r, d
         {
             const float *src = grp == 0 ? sJ : sI;
-            float pr[32];
+            const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int s = 0; s < S; s += 8) {
                 float x[8], y[8], z[8];
@@ -266,82 +350,103 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
                 tc::ldg256(src + 64 + s, y);
                 tc::ldg256(src + 96 + s, z);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) pr[s + u] = fmaf(g.z, z[u], fmaf(g.y, y[u], g.x * x[u]));
-            }
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                if (SPLIT) tc::split_bf16x2(pr[2 * u], pr[2 * u + 1], hi[u], lo[u]);
-                else hi[u] = tc::pack_bf16x2(pr[2 * u], pr[2 * u + 1]);
+                for (int u = 0; u < 8; u += 2) {
+                    const u64 pr = fma2(gz, pk2(z[u], z[u + 1]), fma2(gy, pk2(y[u], y[u + 1]), mul2(gx, pk2(x[u], x[u + 1]))));
+                    split2<SPLIT>(pr, kc, hi[(s + u) >> 1], lo[(s + u) >> 1]);
+                }
             }
             tc::tmem_st16(tlane + TY + 16 * grp, hi);
             if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16 * grp, lo);
             if (grp == 1) {
                 uint32_t hd[8], ld[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) hd[u] = ld[u] = 0u;
-                if (SPLIT) tc::split_bf16x2(g.w, 0.f, hd[0], ld[0]); else hd[0] = tc::pack_bf16x2(g.w, 0.f);
+                for (int u = 0; u < 8; ++u) { hd[u] = ind[u]; ld[u] = 0u; }
+                uint32_t dh, dl = 0u;
+                split2<SPLIT>(pk2(g.w, 0.f), kc, dh, dl);
+                hd[0] |= dh;
+                ld[0] = dl;
                 tc::tmem_st8(tlane + TY + 32, hd);
                 if (SPLIT) tc::tmem_st8(tlane + TY + 72, ld);
             }
         }
+        if (UMMA) {      // U_i (already scaled by log2 e) as three bf16 planes -> rows 65 + 3 a + p of B1
+#pragma unroll
+            for (int m = 0; m < TA / 2; ++m) {
+                const int v = ht + 256 * m, a = v >> 7, n = v & 127;
+                const int ia = min(tile * TA + a, n_atoms - 1);
+                const float u0 = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + n);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(u0);
+                const float r1 = u0 - __bfloat162float(h0);
+                const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+                const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+                const __nv_bfloat16 hp[3] = {h0, h1, h2};
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int kk = 1 + 3 * a + p;        // row 64 + kk; rows 64..71 in K group 0, 72..79 in K group 1
+                    *reinterpret_cast<__nv_bfloat16 *>(ext_hi + (kk >> 3) * 2048 + n * 16 + (kk & 7) * 2) = hp[p];
+                }
+            }
+            tc::fence_async_smem();
+        }
         tc::wait_st();
         tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {                                                  // M1: D1 (X) = A1 . B1^T, K = 80
+        bar_named(bar_id, HALF_THREADS);
+        if (ht == 0) {                                                   // M1: D1 (X) = A1 . B1^T, K = 80
             tc::fence_after_sync();
             const uint32_t idesc = tc::idesc_bf16(128, 128);
             const uint32_t lbo = 128u * 16u;
 #pragma unroll 1
             for (int s = 0; s < 5; ++s) {
-                const uint32_t koff = (uint32_t)s * 2u * lbo;
-                const uint64_t dh = tc::smem_desc(img_hi + tcimg::B1 + koff, lbo, 128u);
+                const uint32_t bh = s < 4 ? img_hi + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_hi_s;
+                const uint32_t bl = s < 4 ? img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_lo_s;
+                const uint64_t dh = tc::smem_desc(bh, lbo, 128u);
                 tc::umma_ts(tbase + TX, tbase + TY + 8u * s, dh, idesc, s > 0);
                 if (SPLIT) {
                     tc::umma_ts(tbase + TX, tbase + TY + 40u + 8u * s, dh, idesc, 1u);
-                    tc::umma_ts(tbase + TX, tbase + TY + 8u * s, tc::smem_desc(img_lo + tcimg::B1 + koff, lbo, 128u), idesc, 1u);
+                    tc::umma_ts(tbase + TX, tbase + TY + 8u * s, tc::smem_desc(bl, lbo, 128u), idesc, 1u);
                 }
             }
             tc::umma_commit(bar);
         }
-        // prefetch the per-atom factors of this thread's first E1 chunk while the tensor core works
-        float pu[4][8], pt[4][8];
+        // prefetch the neighbour factors of this thread's first E1 chunk while the tensor core works
+        float pt[4][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            tc::ldg256(cI + 64 * grp + 8 * u, pu[u]);
-            tc::ldg256(tJ + 64 * grp + 8 * u, pt[u]);
-        }
+        for (int u = 0; u < 4; ++u) tc::ldg256(tJ + 64 * grp + 8 * u, pt[u]);
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
         tc::fence_after_sync();
 
-        // ---------------------------------------------------------------- E1: h1 = ELU(D1 + U_i + T_j) -> A2 (X, in place)
+        // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = 2 * grp + cc;
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX + 32 * c, r);
-            float x[32];
+            u64 y[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int w = 0; w < 8; ++w) x[8 * u + w] = pu[u][w] + pt[u][w];
+            for (int u = 0; u < 16; ++u) y[u] = pk2(pt[u >> 2][2 * (u & 3)], pt[u >> 2][2 * (u & 3) + 1]);
             if (cc == 0) {
 #pragma unroll
+                for (int u = 0; u < 4; ++u) tc::ldg256(tJ + 32 * (c + 1) + 8 * u, pt[u]);
+            }
+            if (!UMMA) {
+#pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    tc::ldg256(cI + 32 * (c + 1) + 8 * u, pu[u]);
-                    tc::ldg256(tJ + 32 * (c + 1) + 8 * u, pt[u]);
+                    float pu[8];
+                    tc::ldg256(cI + 32 * c + 8 * u, pu);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) y[4 * u + w] = add2(y[4 * u + w], pk2(pu[2 * w], pu[2 * w + 1]));
                 }
             }
             tc::wait_ld();
 #pragma unroll
-            for (int u = 0; u < 32; ++u) x[u] = elu_fast(x[u] + __uint_as_float(r[u]));
-            store_activation_chunk<SPLIT>(tlane + TX + 32 * c, x);
+            for (int u = 0; u < 16; ++u) y[u] = add2(y[u], pk2u(r[2 * u], r[2 * u + 1]));
+            activate_store<SPLIT>(tlane + TX + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {                                                  // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
+        bar_named(bar_id, HALF_THREADS);
+        if (ht == 0) {                                                   // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
             tc::fence_after_sync();
             issue_gemm<SPLIT>(tbase, TY + 0, TX + 0, 16, 2, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q, 32);
             issue_gemm<SPLIT>(tbase, TY + 32, TX + 32, 16, 2, img_hi + tcimg::B2P, img_lo + tcimg::B2P, 32);
@@ -359,21 +464,19 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             uint32_t r[32];
             tc::tmem_ld32(tlane + TY + 32 * c, r);
             tc::wait_ld();
-            float x[32];
+            u64 y[16];
 #pragma unroll
-            for (int u = 0; u < 32; u += 4) {
-                const float4 bb = *reinterpret_cast<const float4 *>(b2 + 32 * c + u);
-                x[u + 0] = elu_fast(__uint_as_float(r[u + 0]) + bb.x);
-                x[u + 1] = elu_fast(__uint_as_float(r[u + 1]) + bb.y);
-                x[u + 2] = elu_fast(__uint_as_float(r[u + 2]) + bb.z);
-                x[u + 3] = elu_fast(__uint_as_float(r[u + 3]) + bb.w);
+            for (int u = 0; u < 16; u += 2) {
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b2 + 32 * c + 2 * u);
+                y[u] = add2(pk2u(r[2 * u], r[2 * u + 1]), bb.x);
+                y[u + 1] = add2(pk2u(r[2 * u + 2], r[2 * u + 3]), bb.y);
             }
-            store_activation_chunk<SPLIT>(tlane + TY + 32 * c, x);
+            activate_store<SPLIT>(tlane + TY + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {                                                  // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
+        bar_named(bar_id, HALF_THREADS);
+        if (ht == 0) {                                                   // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
             tc::fence_after_sync();
             issue_gemm<SPLIT>(tbase, TX + 0, TY + 0, 16, 2, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q, 16);
             issue_gemm<SPLIT>(tbase, TX + 16, TY + 32, 16, 2, img_hi + tcimg::B3P, img_lo + tcimg::B3P, 16);
@@ -382,7 +485,7 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         }
         // queries of the centre atom while the tensor core works: [t][h][k] = t*6 + h*3 + k, pre-divided by sdk
         float qv[12];
-        {
+        if (grp == 0) {
             const float *Qi = cI + NODE_C_Q;
 #pragma unroll
             for (int u = 0; u < 12; u += 4) {
@@ -394,9 +497,10 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
         phase ^= 1u;
         tc::fence_after_sync();
 
-        // ---------------------------------------------------------------- E3: attention (both groups compute the weights)
-        float wq[NH], wp0[NH], wp1s[NH];
-        {
+        // ---------------------------------------------------------------- E3
+        if (grp == 0) {
+            // attention weights of this edge (src/model_operations.py:139-140) -> Ws row, every weight duplicated
+            // into a pair so that the reduction below can use packed FMAs without register shuffling
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX, r);                               // [0,3) Kq, [16,25) Kp
             tc::wait_ld();
@@ -420,10 +524,10 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             mx[2] = seg_max_tc<SEG>(fmaxf(lp[0][0], fmaxf(lp[0][1], lp[0][2])));
             mx[3] = seg_max_tc<SEG>(fmaxf(lp[1][0], fmaxf(lp[1][1], lp[1][2])));
             if (WPA == 2) {
-                if (lane == 0) { redg[quarter * 8 + 0] = mx[0]; redg[quarter * 8 + 1] = mx[1]; redg[quarter * 8 + 2] = mx[2]; redg[quarter * 8 + 3] = mx[3]; }
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], redg[(quarter ^ 1) * 8 + u]);
+                if (lane == 0) *reinterpret_cast<float4 *>(red + quarter * 8) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+                bar_named(bar_g0, 128);
+                const float4 o = *reinterpret_cast<const float4 *>(red + (quarter ^ 1) * 8);
+                mx[0] = fmaxf(mx[0], o.x); mx[1] = fmaxf(mx[1], o.y); mx[2] = fmaxf(mx[2], o.z); mx[3] = fmaxf(mx[3], o.w);
             }
             float eq[NH], ep[NH][3], sm[4];
 #pragma unroll
@@ -437,127 +541,130 @@ edge_kernel_tc(const float *__restrict__ lw, const unsigned char *__restrict__ t
             sm[2] = seg_sum_tc<SEG>(ep[0][0] + ep[0][1] + ep[0][2]);
             sm[3] = seg_sum_tc<SEG>(ep[1][0] + ep[1][1] + ep[1][2]);
             if (WPA == 2) {
-                if (lane == 0) { redg[quarter * 8 + 4] = sm[0]; redg[quarter * 8 + 5] = sm[1]; redg[quarter * 8 + 6] = sm[2]; redg[quarter * 8 + 7] = sm[3]; }
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) sm[u] += redg[(quarter ^ 1) * 8 + 4 + u];
+                if (lane == 0) *reinterpret_cast<float4 *>(red + quarter * 8 + 4) = make_float4(sm[0], sm[1], sm[2], sm[3]);
+                bar_named(bar_g0, 128);
+                const float4 o = *reinterpret_cast<const float4 *>(red + (quarter ^ 1) * 8 + 4);
+                sm[0] += o.x; sm[1] += o.y; sm[2] += o.z; sm[3] += o.w;
             }
+            const float iq0 = 1.0f / sm[0], iq1 = 1.0f / sm[1], ip0 = 1.0f / sm[2], ip1 = 1.0f / sm[3];
+            const float wq0 = eq[0] * iq0, wq1 = eq[1] * iq1;                     // Mq[h]
+            const float wv0 = ep[0][0] * ip0, wv1 = ep[1][0] * ip1;               // Mp[h, token V1 (x) r]
+            const float wi0 = ep[0][1] * ip0, wi1 = ep[1][1] * ip1;               // Mp[h, token p_i]
+            const float wj0 = ep[0][2] * ip0, wj1 = ep[1][2] * ip1;               // Mp[h, token p_j]
+            float4 *row = reinterpret_cast<float4 *>(Ws + e * WS_STRIDE);
+            const int sw = e & 7;                                                 // 16-byte chunk swizzle
+            row[0 ^ sw] = make_float4(wq0, wq0, wq1, wq1);
+            row[1 ^ sw] = make_float4(wj0, wj0, wj1, wj1);
+            row[2 ^ sw] = make_float4(wv0 * g.x, wv0 * g.x, wv0 * g.y, wv0 * g.y);
+            row[3 ^ sw] = make_float4(wv0 * g.z, wv0 * g.z, wv1 * g.x, wv1 * g.x);
+            row[4 ^ sw] = make_float4(wv1 * g.y, wv1 * g.y, wv1 * g.z, wv1 * g.z);
+            row[5 ^ sw] = make_float4(wi0, wi1, __int_as_float(j), 0.f);
+        } else {
+            // V0 | V1 (+ bias) of this edge -> Vs row
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                const float iq = 1.0f / sm[h], ip = 1.0f / sm[2 + h];
-                wq[h] = eq[h] * iq;                    // Mq[h]
-                wp0[h] = ep[h][0] * ip;                // Mp[h, token V1 (x) r]
-                wp1s[h] = seg_sum_tc<SEG>(ep[h][1] * ip);   // sum over this warp's edges of Mp[h, token p_i]
-            }
-            if (grp == 0)                              // the p_j token is summed warp-per-atom below (coalesced rows)
-                *reinterpret_cast<float4 *>(Ws + 4 * e) = make_float4(ep[0][2] / sm[2], ep[1][2] / sm[3], __int_as_float(j), 0.f);
-        }
-        // weighted sums, reduced over the atom's edges; lane keeps EPL elements per 32-vector.
-        // group 0: Zq (2 vectors) + Zp[c=0] (2 vectors); group 1: Zp[c=1], Zp[c=2] (4 vectors)
-        float *zw = Zs + (quarter * APW + (lane / SEG)) * 256 + (lane % SEG) * EPL;
-        if (grp == 0) {
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TX + 32, r);                          // V0
-            tc::wait_ld();
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tc::tmem_ld32(tlane + TX + 32 + 32 * half, r);
+                tc::wait_ld();
+                float4 *dst = reinterpret_cast<float4 *>(Vs + e * VS_STRIDE + 32 * half);
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {                              // Zq = Mq . V0   (src/model_operations.py:143)
-                float v[32];
-#pragma unroll
-                for (int u = 0; u < 32; ++u) v[u] = wq[h] * (__uint_as_float(r[u]) + b3[32 + u]);
-                transpose_reduce<SEG>(v, lane);
-#pragma unroll
-                for (int t = 0; t < EPL; ++t) zw[h * 32 + t] = v[t];
-            }
-        }
-        {
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TX + 64, r);                          // V1
-            tc::wait_ld();
-            float v1[32];
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v1[u] = __uint_as_float(r[u]) + b3[64 + u];
-            const float gr[3] = {g.x, g.y, g.z};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {                               // Zp = Mp . [V1 (x) r ; p_i ; p_j]   (:131-136, :144)
-                if ((c == 0) != (grp == 0)) continue;                   // warp-uniform
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    float v[32];
-                    const float a0 = wp0[h] * gr[c];
-#pragma unroll
-                    for (int u = 0; u < 32; ++u) v[u] = a0 * v1[u];
-                    transpose_reduce<SEG>(v, lane);
-#pragma unroll
-                    for (int t = 0; t < EPL; ++t) {
-                        const float pi = __ldg(sI + 32 + 32 * c + (lane % SEG) * EPL + t);
-                        zw[64 + c * 64 + h * 32 + t] = fmaf(wp1s[h], pi, v[t]);
-                    }
+                for (int u = 0; u < 8; ++u) {
+                    const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b3 + 32 + 32 * half + 4 * u);
+                    ulonglong2 o;
+                    o.x = add2(pk2u(r[4 * u], r[4 * u + 1]), bb.x);
+                    o.y = add2(pk2u(r[4 * u + 2], r[4 * u + 3]), bb.y);
+                    *reinterpret_cast<ulonglong2 *>(dst + u) = o;
                 }
             }
         }
-        if (tile + (int)gridDim.x < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
-            const int in = min((tile + (int)gridDim.x) * TA + a_loc, n_atoms - 1);
+        if (tile + tstride < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
+            const int in = min((tile + tstride) * TA + a_loc, n_atoms - 1);
             j_next = ids32[(size_t)in * KMAX + k];
             g_next = geom[(size_t)in * KMAX + k];
         }
         tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
-        __syncthreads();
+        bar_named(bar_id, HALF_THREADS);
 
-        // ---------------------------------------------------------------- attention sums Z -> global
-        // work unit = (atom, part): part 0 = Zq (64 values), parts 1..3 = Zp[c] incl. the p_j token, summed here with
-        // lane = channel and one coalesced 128 B row per edge.  The per-atom projections qpm / ppm run in the next
-        // node kernel, where their weights are reused across 8 atoms.
-        for (int unit = warp; unit < TA * 4; unit += TC_THREADS / 32) {
-            const int a = unit >> 2, part = unit & 3;
-            const int ia = tile * TA + a;
-            if (ia >= n_atoms) continue;
-            const float *z0 = Zs + (WPA == 2 ? a * 2 : a) * 256 + part * 64;
-            float zq0 = z0[lane], zq1 = z0[32 + lane];
-            if (WPA == 2) { zq0 += z0[256 + lane]; zq1 += z0[256 + 32 + lane]; }
-            if (part > 0) {
-                const float *ws = Ws + 4 * (a * NN);
-                constexpr int PB = NN < 16 ? NN : 16;          // independent row loads in flight per batch
-#pragma unroll 1
-                for (int e0 = 0; e0 < NN; e0 += PB) {
-                    float4 w4[PB];
-                    float pj[PB];
+        // ---------------------------------------------------------------- R: attention-weighted sums over the edges
+        // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
+        {
+            const int pair = ht & 15, rg = ht >> 4;
+            const int ia = min(tile * TA + (rg * 8) / NN, n_atoms - 1);
+            const float *pI = state_in + (size_t)(ia + 1) * SR + 32 + 2 * pair;
+            u64 zq[2], zp[3][2], wi = 0ull;
+            zq[0] = zq[1] = 0ull;
 #pragma unroll
-                    for (int u = 0; u < PB; ++u) w4[u] = *reinterpret_cast<const float4 *>(ws + 4 * (e0 + u));
+            for (int c = 0; c < 3; ++c) zp[c][0] = zp[c][1] = 0ull;
+            const float *vrow = Vs + (rg * 8) * VS_STRIDE + 2 * pair;
+            const float *wrow = Ws + (rg * 8) * WS_STRIDE;
 #pragma unroll
-                    for (int u = 0; u < PB; ++u)
-                        pj[u] = __ldg(state_in + (size_t)__float_as_int(w4[u].z) * SR + part * 32 + lane);
+            for (int ee = 0; ee < 8; ++ee) {
+                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wrow + ee * WS_STRIDE);
+                const ulonglong2 c0 = wr[0 ^ ee], c1 = wr[1 ^ ee], c2 = wr[2 ^ ee], c3 = wr[3 ^ ee], c4 = wr[4 ^ ee], c5 = wr[5 ^ ee];
+                const int jj = (int)(uint32_t)(c5.y & 0xffffffffull);
+                const float *pJ = state_in + (size_t)jj * SR + 32 + 2 * pair;
+                const u64 v0 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE);
+                const u64 v1 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE + 32);
+                u64 pj[3];
 #pragma unroll
-                    for (int u = 0; u < PB; ++u) {
-                        zq0 = fmaf(w4[u].x, pj[u], zq0);
-                        zq1 = fmaf(w4[u].y, pj[u], zq1);
-                    }
+                for (int c = 0; c < 3; ++c) pj[c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
+                zq[0] = fma2(c0.x, v0, zq[0]);
+                zq[1] = fma2(c0.y, v0, zq[1]);
+                zp[0][0] = fma2(c2.x, v1, zp[0][0]);
+                zp[1][0] = fma2(c2.y, v1, zp[1][0]);
+                zp[2][0] = fma2(c3.x, v1, zp[2][0]);
+                zp[0][1] = fma2(c3.y, v1, zp[0][1]);
+                zp[1][1] = fma2(c4.x, v1, zp[1][1]);
+                zp[2][1] = fma2(c4.y, v1, zp[2][1]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    zp[c][0] = fma2(c1.x, pj[c], zp[c][0]);
+                    zp[c][1] = fma2(c1.y, pj[c], zp[c][1]);
                 }
+                wi = add2(wi, c5.x);
             }
-            float *zo = Zout + (size_t)(ia + 1) * 256 + part * 64;
-            zo[lane] = zq0;
-            zo[32 + lane] = zq1;
+            float wi0, wi1;
+            up2(wi, wi0, wi1);
+            const u64 w0 = pk2(wi0, wi0), w1 = pk2(wi1, wi1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const u64 pi = __ldg(reinterpret_cast<const u64 *>(pI + 32 * c));
+                zp[c][0] = fma2(w0, pi, zp[c][0]);
+                zp[c][1] = fma2(w1, pi, zp[c][1]);
+            }
+            bar_named(bar_id, HALF_THREADS);          // every read of Vs is done: the partial sums P alias it
+            u64 *P = reinterpret_cast<u64 *>(Vs + rg * 256 + 2 * pair);
+            P[0] = zq[0];
+            P[16] = zq[1];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                P[32 + 32 * c] = zp[c][0];
+                P[48 + 32 * c] = zp[c][1];
+            }
+            bar_named(bar_id, HALF_THREADS);
+            // Z record of atom a: [Zq h*32+s | Zp c*64 + h*32 + s]; the per-atom projections qpm / ppm run in the next
+            // node kernel, where their weights are reused across 8 atoms
+#pragma unroll
+            for (int a = 0; a < TA; ++a) {
+                float z = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < GA; ++gg) z += Vs[(a * GA + gg) * 256 + ht];
+                const int io = tile * TA + a;
+                if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
+            }
         }
-        __syncthreads();
-        tc::fence_after_sync();
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tbase, TM_COLS);
-}
-
-template <int NN>
-constexpr size_t tc_smem_bytes() {
-    constexpr int SEG = NN < 32 ? NN : 32;
-    return (size_t)tcimg::TOTAL + (size_t)(4 * (32 / SEG) * 256 + 64 + 128 * 4) * sizeof(float) + 32;
+    if (tid < 32) tc::tmem_dealloc(*tmem_slot, TM_COLS);
 }
 
 template <int NN, bool SPLIT>
-int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom,
-                   const float *state_in, const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
+int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
+                   const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
     static int configured = 0, n_sm = 0;
-    constexpr size_t smem = tc_smem_bytes<NN>();
     if (!configured) {
-        PESTO_CUDA(cudaFuncSetAttribute(edge_kernel_tc<NN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PESTO_CUDA(cudaFuncSetAttribute(edge_kernel_tc<NN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         int dev = 0;
         PESTO_CUDA(cudaGetDevice(&dev));
         PESTO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -565,9 +672,9 @@ int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t 
     }
     constexpr int TA = 128 / NN;
     const int n_tiles = (n_atoms + TA - 1) / TA;
-    const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
-    edge_kernel_tc<NN, SPLIT><<<grid, TC_THREADS, smem, st>>>(lw, (const unsigned char *)tcw, n_atoms, ids32,
-                                                            (const float4 *)geom, state_in, nodeT, nodeC, Zout);
+    const int grid = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
+    edge_kernel_tc<NN, SPLIT><<<grid, CTA_THREADS, SM_TOTAL, st>>>((const unsigned char *)tcw, n_atoms, ids32,
+                                                                 (const float4 *)geom, state_in, nodeT, nodeC, Zout);
     PESTO_CUDA(cudaGetLastError());
     if (getenv("PESTO_TC_DEBUG")) {       // debugging aid: synchronise and report a timed-out tensor-core stage
         PESTO_CUDA(cudaStreamSynchronize(st));
@@ -584,13 +691,13 @@ int launch_edge_tc(const float *lw, const void *tcw, int n_atoms, const int32_t 
 }
 
 template <bool SPLIT>
-int dispatch_tc(int nn, const float *lw, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom,
-                const float *state_in, const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
+int dispatch_tc(int nn, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
+                const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
     switch (nn) {
-        case 8:  return launch_edge_tc<8, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 16: return launch_edge_tc<16, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 32: return launch_edge_tc<32, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 64: return launch_edge_tc<64, SPLIT>(lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 8:  return launch_edge_tc<8, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 16: return launch_edge_tc<16, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 32: return launch_edge_tc<32, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 64: return launch_edge_tc<64, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
         default:
             set_error("state_update: unsupported nn=%d (supported: 8, 16, 32, 64)", nn);
             return PESTO_EINVAL;
@@ -610,8 +717,8 @@ int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, 
     const int n_rows = n_atoms + 1;
     float *nodeT = node_scratch;
     float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
-    return mode == PESTO_MODE_BF16X3 ? dispatch_tc<true>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st)
-                                     : dispatch_tc<false>(nn, lw, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st);
+    return mode == PESTO_MODE_BF16X3 ? dispatch_tc<true>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st)
+                                     : dispatch_tc<false>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st);
 }
 
 // One complete layer state_in -> state_out (staged API, three launches): head factors, edge kernel, per-atom tail.

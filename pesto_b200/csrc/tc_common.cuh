@@ -68,23 +68,25 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a tensor-core stage that never completes must not hang the GPU.  On timeout the stage id is
+// Bounded wait: a tensor-core stage that never completes must not hang the GPU.  On timeout the stage id is
 // recorded in *watchdog (global memory) and the caller carries on with garbage; hosts check the flag.
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *watchdog = nullptr, int stage = 0) {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 20); ++spin)
         if (mbar_try_wait(bar, parity)) return true;
     if (watchdog) atomicMax(watchdog, stage);
     return false;
