@@ -118,19 +118,25 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 H, 256 H + 256): X = +0, Y = +128
 constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
-constexpr int WS_STRIDE = 32;         // floats per edge row of the attention-weight buffer (128 B, chunk-swizzled)
+constexpr int WS_STRIDE = 28;         // floats per edge row of the attention-weight buffer (112 B: conflict-free STS.128)
+constexpr int TS_STRIDE = 132;        // floats per staged T_j row (528 B: conflict-free row-per-lane LDS.128)
 
-// per-half shared memory (byte offsets)
-constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64..79, hi plane: W_d | per-tile U planes
-constexpr int HS_EXT_LO = HS_EXT_HI + 4096;                   // same rows, lo plane (W_d only)
-constexpr int HS_VS = HS_EXT_LO + 4096;                       // [128][VS_STRIDE] fp32; aliased by the partial sums P
+// per-half shared memory (byte offsets).  Region G is time-shared inside a tile: the neighbour factors T_j of the
+// tile's 128 edges (bulk-copied while the previous stages run, read in E1), then V0|V1 and the attention weights
+// (written in E3, read in R), then the partial sums P of R.
+constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64..79: W_d (hi), U planes per tile, W_d (lo)
+constexpr int HS_G = HS_EXT_HI + 4096;
+constexpr int HS_TS = HS_G;                                   // [128][TS_STRIDE] fp32
+constexpr int HS_VS = HS_G;                                   // [128][VS_STRIDE] fp32; aliased by the partial sums P
 constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [128][WS_STRIDE] fp32
-constexpr int HS_RED = HS_WS + 128 * WS_STRIDE * 4;           // [4 quarters][8] softmax exchange (nn = 64)
+constexpr int HS_RED = HS_G + 128 * TS_STRIDE * 4;            // [4 quarters][8] softmax exchange (nn = 64)
 constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;
+static_assert(HS_WS + 128 * WS_STRIDE * 4 <= HS_RED, "V / weight buffers fit into the T staging region");
 constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
 constexpr int SM_HALF0 = SM_PAT + 128;
-constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // 2 mbarriers + TMEM slot
-constexpr int SM_TOTAL = SM_BAR + 32;
+constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // 2 MMA mbarriers, 2 T-copy mbarriers, TMEM slot
+constexpr int SM_TOTAL = SM_BAR + 48;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget of one CTA per SM");
 static_assert(SM_HALF0 % 128 == 0 && HS_BYTES % 128 == 0, "per-half regions stay 128-byte aligned");
 
 typedef unsigned long long u64;
@@ -267,25 +273,32 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int grp = hwarp >> 2, quarter = hwarp & 3;       // column group, TMEM lane quarter
     unsigned char *hs = smem_raw + SM_HALF0 + H * HS_BYTES;
     unsigned char *ext_hi = hs + HS_EXT_HI;
+    float *Ts = reinterpret_cast<float *>(hs + HS_TS);
     float *Vs = reinterpret_cast<float *>(hs + HS_VS);
     float *Ws = reinterpret_cast<float *>(hs + HS_WS);
     float *red = reinterpret_cast<float *>(hs + HS_RED);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 16);
+    uint64_t *tbar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 2 + H;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 32);
 
     if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
     if (tid == 0) {
         tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR), 1);
         tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 1, 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 2, 1);
+        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 3, 1);
         tc::fence_mbar_init();
     }
     for (int u = tid; u < tcimg::TOTAL / 16; u += CTA_THREADS)
         reinterpret_cast<uint4 *>(img)[u] = __ldg(reinterpret_cast<const uint4 *>(tcw) + u);
-    {   // rows k = 64..79 of B1 (distance column + zeros) -> the per-half, per-tile mutable copies
-        const uint4 *src_hi = reinterpret_cast<const uint4 *>(tcw + tcimg::B1 + 8 * 2048);
-        const uint4 *src_lo = reinterpret_cast<const uint4 *>(tcw + tcimg::IMG + tcimg::B1 + 8 * 2048);
-        reinterpret_cast<uint4 *>(hs + HS_EXT_HI)[ht] = __ldg(src_hi + ht);
-        reinterpret_cast<uint4 *>(hs + HS_EXT_LO)[ht] = __ldg(src_lo + ht);
+    {   // rows k = 64..79 of B1 -> the per-half, per-tile mutable copy: row 64 = W_d (hi plane), rows 65..76 = U planes
+        // (per tile), row 77 = W_d (lo plane; the distance enters twice, so this K step needs no lo-plane MMA)
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(tcw + tcimg::B1 + 8 * 2048) + ht);
+        if (ht >= 128) {
+            const uint32_t wl = __ldg(reinterpret_cast<const uint32_t *>(tcw + tcimg::IMG + tcimg::B1 + 8 * 2048 + (ht - 128) * 16));
+            v.z = (v.z & 0x0000ffffu) | ((wl & 0xffffu) << 16);                         // k = 77: element 5 of K group 1
+        }
+        reinterpret_cast<uint4 *>(hs + HS_EXT_HI)[ht] = v;
     }
     if (tid < 32) {      // indicator words: column k = 65 + 3 a + p (p < 3) carries plane p of U of the tile's atom a
         const int a = tid >> 3, u = tid & 7;
@@ -304,9 +317,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const uint32_t tbase = *tmem_slot + (uint32_t)H * 256u;
     const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
     const uint32_t img_hi = tc::smem_u32(img), img_lo = img_hi + tcimg::IMG;
-    const uint32_t ext_hi_s = tc::smem_u32(hs + HS_EXT_HI), ext_lo_s = tc::smem_u32(hs + HS_EXT_LO);
+    const uint32_t ext_hi_s = tc::smem_u32(hs + HS_EXT_HI);
     const int bar_id = 1 + H, bar_g0 = 3 + H;
-    uint32_t phase = 0;
+    uint32_t phase = 0, tphase = 0;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
     PairConsts kc;
     kc.neg1 = pk2(-1.f, -1.f);
@@ -326,6 +339,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
         j_next = ids32[(size_t)i0 * KMAX + k];
         g_next = geom[(size_t)i0 * KMAX + k];
+        // neighbour factors T_j of the first tile -> shared memory (one 512-byte bulk copy per edge)
+        if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
+        if (grp == 0) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
     }
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
@@ -334,9 +350,17 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         const float *sI = state_in + (size_t)(i + 1) * SR;
         const float *sJ = state_in + (size_t)j * SR;
         const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
-        const float *tJ = nodeT + (size_t)j * NODE_T_STRIDE;
 
-        // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a)] -> TMEM (Y)
+        float u0v[UMMA ? TA / 2 : 1];
+        if (UMMA) {      // U_i of the tile's atoms (consumed at the end of S0)
+#pragma unroll
+            for (int m = 0; m < TA / 2; ++m) {
+                const int v = ht + 256 * m;
+                const int ia = min(tile * TA + (v >> 7), n_atoms - 1);
+                u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + (v & 127));
+            }
+        }
+        // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y)
         // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
         // group 0: p_j.r, group 1: p_i.r, d
         {
@@ -363,8 +387,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 for (int u = 0; u < 8; ++u) { hd[u] = ind[u]; ld[u] = 0u; }
                 uint32_t dh, dl = 0u;
                 split2<SPLIT>(pk2(g.w, 0.f), kc, dh, dl);
-                hd[0] |= dh;
+                hd[0] |= dh;                 // k = 64 (x W_d hi) and k = 77 (x W_d lo)
+                hd[6] |= dh << 16;
                 ld[0] = dl;
+                ld[6] = dl << 16;
                 tc::tmem_st8(tlane + TY + 32, hd);
                 if (SPLIT) tc::tmem_st8(tlane + TY + 72, ld);
             }
@@ -373,8 +399,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int m = 0; m < TA / 2; ++m) {
                 const int v = ht + 256 * m, a = v >> 7, n = v & 127;
-                const int ia = min(tile * TA + a, n_atoms - 1);
-                const float u0 = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + n);
+                const float u0 = u0v[m];
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(u0);
                 const float r1 = u0 - __bfloat162float(h0);
                 const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
@@ -398,20 +423,19 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll 1
             for (int s = 0; s < 5; ++s) {
                 const uint32_t bh = s < 4 ? img_hi + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_hi_s;
-                const uint32_t bl = s < 4 ? img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_lo_s;
                 const uint64_t dh = tc::smem_desc(bh, lbo, 128u);
                 tc::umma_ts(tbase + TX, tbase + TY + 8u * s, dh, idesc, s > 0);
                 if (SPLIT) {
                     tc::umma_ts(tbase + TX, tbase + TY + 40u + 8u * s, dh, idesc, 1u);
-                    tc::umma_ts(tbase + TX, tbase + TY + 8u * s, tc::smem_desc(bl, lbo, 128u), idesc, 1u);
+                    if (s < 4)
+                        tc::umma_ts(tbase + TX, tbase + TY + 8u * s,
+                                    tc::smem_desc(img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
                 }
             }
             tc::umma_commit(bar);
         }
-        // prefetch the neighbour factors of this thread's first E1 chunk while the tensor core works
-        float pt[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) tc::ldg256(tJ + 64 * grp + 8 * u, pt[u]);
+        if (alive) alive = tc::mbar_wait(tbar, tphase, &g_tc_watchdog, 4);      // the tile's T_j rows have landed
+        tphase ^= 1u;
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
         tc::fence_after_sync();
@@ -424,10 +448,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             tc::tmem_ld32(tlane + TX + 32 * c, r);
             u64 y[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) y[u] = pk2(pt[u >> 2][2 * (u & 3)], pt[u >> 2][2 * (u & 3) + 1]);
-            if (cc == 0) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) tc::ldg256(tJ + 32 * (c + 1) + 8 * u, pt[u]);
+            for (int u = 0; u < 8; ++u) {
+                const ulonglong2 t2 = *reinterpret_cast<const ulonglong2 *>(Ts + e * TS_STRIDE + 32 * c + 4 * u);
+                y[2 * u] = t2.x;
+                y[2 * u + 1] = t2.y;
             }
             if (!UMMA) {
 #pragma unroll
@@ -483,7 +507,16 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             issue_gemm<SPLIT>(tbase, TX + 32, TY + 64, 16, 4, img_hi + tcimg::B3V, img_lo + tcimg::B3V, 64);
             tc::umma_commit(bar);
         }
-        // queries of the centre atom while the tensor core works: [t][h][k] = t*6 + h*3 + k, pre-divided by sdk
+        // neighbour ids of this thread's 8-edge reduction group (phase R), while the tensor core works
+        const int pair = ht & 15, rg = ht >> 4;
+        const int iaR = min(tile * TA + (rg * 8) / NN, n_atoms - 1);
+        int4 idr[2];
+        {
+            const int4 *idp = reinterpret_cast<const int4 *>(ids32 + (size_t)iaR * KMAX + (rg * 8) % NN);
+            idr[0] = __ldg(idp);
+            idr[1] = __ldg(idp + 1);
+        }
+        // queries of the centre atom: [t][h][k] = t*6 + h*3 + k, pre-divided by sdk
         float qv[12];
         if (grp == 0) {
             const float *Qi = cI + NODE_C_Q;
@@ -552,13 +585,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             const float wi0 = ep[0][1] * ip0, wi1 = ep[1][1] * ip1;               // Mp[h, token p_i]
             const float wj0 = ep[0][2] * ip0, wj1 = ep[1][2] * ip1;               // Mp[h, token p_j]
             float4 *row = reinterpret_cast<float4 *>(Ws + e * WS_STRIDE);
-            const int sw = e & 7;                                                 // 16-byte chunk swizzle
-            row[0 ^ sw] = make_float4(wq0, wq0, wq1, wq1);
-            row[1 ^ sw] = make_float4(wj0, wj0, wj1, wj1);
-            row[2 ^ sw] = make_float4(wv0 * g.x, wv0 * g.x, wv0 * g.y, wv0 * g.y);
-            row[3 ^ sw] = make_float4(wv0 * g.z, wv0 * g.z, wv1 * g.x, wv1 * g.x);
-            row[4 ^ sw] = make_float4(wv1 * g.y, wv1 * g.y, wv1 * g.z, wv1 * g.z);
-            row[5 ^ sw] = make_float4(wi0, wi1, __int_as_float(j), 0.f);
+            row[0] = make_float4(wq0, wq0, wq1, wq1);
+            row[1] = make_float4(wj0, wj0, wj1, wj1);
+            row[2] = make_float4(wv0 * g.x, wv0 * g.x, wv0 * g.y, wv0 * g.y);
+            row[3] = make_float4(wv0 * g.z, wv0 * g.z, wv1 * g.x, wv1 * g.x);
+            row[4] = make_float4(wv1 * g.y, wv1 * g.y, wv1 * g.z, wv1 * g.z);
+            row[5] = make_float4(wi0, wi1, 0.f, 0.f);
         } else {
             // V0 | V1 (+ bias) of this edge -> Vs row
 #pragma unroll
@@ -582,15 +614,23 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             j_next = ids32[(size_t)in * KMAX + k];
             g_next = geom[(size_t)in * KMAX + k];
         }
-        tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
-        bar_named(bar_id, HALF_THREADS);
-
         // ---------------------------------------------------------------- R: attention-weighted sums over the edges
         // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
         {
-            const int pair = ht & 15, rg = ht >> 4;
-            const int ia = min(tile * TA + (rg * 8) / NN, n_atoms - 1);
-            const float *pI = state_in + (size_t)(ia + 1) * SR + 32 + 2 * pair;
+            // p_j of the group's 8 edges: issued before the barrier so that the gather latency overlaps it
+            u64 pjr[8][3];
+            {
+                const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
+#pragma unroll
+                for (int ee = 0; ee < 8; ++ee) {
+                    const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
+                }
+            }
+            tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
+            bar_named(bar_id, HALF_THREADS);
+            const float *pI = state_in + (size_t)(iaR + 1) * SR + 32 + 2 * pair;
             u64 zq[2], zp[3][2], wi = 0ull;
             zq[0] = zq[1] = 0ull;
 #pragma unroll
@@ -600,14 +640,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int ee = 0; ee < 8; ++ee) {
                 const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wrow + ee * WS_STRIDE);
-                const ulonglong2 c0 = wr[0 ^ ee], c1 = wr[1 ^ ee], c2 = wr[2 ^ ee], c3 = wr[3 ^ ee], c4 = wr[4 ^ ee], c5 = wr[5 ^ ee];
-                const int jj = (int)(uint32_t)(c5.y & 0xffffffffull);
-                const float *pJ = state_in + (size_t)jj * SR + 32 + 2 * pair;
+                const ulonglong2 c0 = wr[0], c1 = wr[1], c2 = wr[2], c3 = wr[3], c4 = wr[4];
+                const u64 c5 = *reinterpret_cast<const u64 *>(wr + 5);
                 const u64 v0 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE);
                 const u64 v1 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE + 32);
-                u64 pj[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) pj[c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
                 zq[0] = fma2(c0.x, v0, zq[0]);
                 zq[1] = fma2(c0.y, v0, zq[1]);
                 zp[0][0] = fma2(c2.x, v1, zp[0][0]);
@@ -618,10 +654,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 zp[2][1] = fma2(c4.y, v1, zp[2][1]);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    zp[c][0] = fma2(c1.x, pj[c], zp[c][0]);
-                    zp[c][1] = fma2(c1.y, pj[c], zp[c][1]);
+                    zp[c][0] = fma2(c1.x, pjr[ee][c], zp[c][0]);
+                    zp[c][1] = fma2(c1.y, pjr[ee][c], zp[c][1]);
                 }
-                wi = add2(wi, c5.x);
+                wi = add2(wi, c5);
             }
             float wi0, wi1;
             up2(wi, wi0, wi1);
@@ -652,6 +688,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 const int io = tile * TA + a;
                 if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
             }
+        }
+        if (tile + tstride < n_tiles) {       // region G is free again: start the bulk copies of the next tile's T_j rows
+            bar_named(bar_id, HALF_THREADS);
+            tc::fence_async_smem();
+            if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
+            if (grp == 0) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
         }
     }
     tc::fence_before_sync();

@@ -92,6 +92,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *w
     return false;
 }
 
+// ---- bulk async copy global -> shared (TMA engine, no tensor map): completes `bytes` on the mbarrier ---------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst (shared), src (global) and bytes must be multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major, no swizzle: element (row n, k) of a bf16 operand lives at
 //     base + (k/8)*lbo + (n/8)*sbo + (n%8)*16 + (k%8)*2   bytes

@@ -5,7 +5,7 @@ tag=${1:-rX}
 out=gpurun_out
 mkdir -p $out
 if [ "$2" != "skip-tests" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
+  PESTO_TC_DEBUG=1 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
   tail -3 $out/${tag}_pytest.log
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?"
