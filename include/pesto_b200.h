@@ -147,6 +147,11 @@ int    pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1
 int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int N, int split,
                            int lbo, int sbo, int idesc, void *stream);
 
+/* Debug: phase timeline of the tensor-core edge kernel.  While buf != NULL, every edge-kernel launch makes CTA 0
+ * write clock64() stamps at 17 phase boundaries per tile to buf[tile][half 0..1][column group 0..1][17] (device
+ * int64) for the first max_tiles tiles of each half; buf == NULL switches it off. */
+int pesto_debug_edge_timeline(void *buf, int max_tiles);
+
 /* number of kernels one pesto_forward / pesto_knn call launches (for bench.py's gpu_launches) */
 int pesto_forward_launch_count(const pesto_model_t *m, int dense_m, int mode);
 int pesto_knn_launch_count(void);

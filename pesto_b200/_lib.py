@@ -39,6 +39,7 @@ SIGNATURES = {
     "pesto_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pesto_forward_launch_count": (_i, [_vp, _i, _i]),
     "pesto_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pesto_debug_edge_timeline": (_i, [_vp, _i]),
 }
 
 _lib = None

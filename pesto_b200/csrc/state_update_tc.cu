@@ -119,6 +119,7 @@ constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 
 constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
 constexpr int WS_STRIDE = 28;         // floats per edge row of the attention-weight buffer (112 B: conflict-free STS.128)
+constexpr int PROF_STAMPS = 17;       // clock stamps per tile of the debug timeline (pesto_debug_edge_timeline)
 constexpr int TS_STRIDE = 132;        // floats per staged T_j row (528 B: conflict-free row-per-lane LDS.128)
 
 // per-half shared memory (byte offsets).  Region G is time-shared inside a tile: the neighbour factors T_j of the
@@ -220,12 +221,13 @@ __device__ __forceinline__ float seg_sum_tc(float v) {
 }
 
 // issue D[d_col .. d_col+N) (+)= A(K columns packed at a_col: hi at +8s, lo at +lo_off+8s per 16-wide K step) . B^T
-template <bool SPLIT>
-__device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, int ksteps,
-                                           uint32_t b_hi, uint32_t b_lo, int N) {
-    const uint32_t idesc = tc::idesc_bf16(128, N);
-    const uint32_t lbo = (uint32_t)N * 16u;
-    for (int s = 0; s < ksteps; ++s) {
+template <bool SPLIT, int KSTEPS, int N>
+__device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t b_hi,
+                                           uint32_t b_lo) {
+    constexpr uint32_t idesc = tc::idesc_bf16(128, N);
+    constexpr uint32_t lbo = (uint32_t)N * 16u;
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) {
         // K steps inside one 32-wide activation chunk are 8 columns apart; chunks are 32 columns apart
         const uint32_t a = tbase + a_col + (uint32_t)(s >> 1) * 32u + (uint32_t)(s & 1) * 8u;
         const uint32_t koff = (uint32_t)s * 2u * lbo;
@@ -256,7 +258,7 @@ template <int NN, bool SPLIT>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t *__restrict__ ids32,
                const float4 *__restrict__ geom, const float *__restrict__ state_in, const float *__restrict__ nodeT,
-               const float *__restrict__ nodeC, float *__restrict__ Zout) {
+               const float *__restrict__ nodeC, float *__restrict__ Zout, long long *__restrict__ prof, int prof_tiles) {
     constexpr int TA = 128 / NN;                    // atoms per tile
     constexpr int SEG = NN < 32 ? NN : 32;          // lanes of one atom inside a warp
     constexpr int WPA = NN / SEG;                   // warps (of one group) per atom: 2 for nn = 64
@@ -314,10 +316,14 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = *tmem_slot + (uint32_t)H * 256u;
+    // warp-uniform copies (shuffles from lane 0 let the compiler keep them in uniform registers: the MMA issue code
+    // then needs no per-instruction vote / broadcast)
+    const int hwarp_u = __shfl_sync(FULLM, hwarp, 0), H_u = __shfl_sync(FULLM, H, 0);
+    const uint32_t tbase = __shfl_sync(FULLM, *tmem_slot, 0) + (uint32_t)H_u * 256u;
     const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t img_hi = tc::smem_u32(img), img_lo = img_hi + tcimg::IMG;
-    const uint32_t ext_hi_s = tc::smem_u32(hs + HS_EXT_HI);
+    const uint32_t img_hi = tc::smem_u32(smem_raw), img_lo = img_hi + tcimg::IMG;
+    const uint32_t ext_hi_s = img_hi + SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI;
+    uint64_t *bar_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
     uint32_t phase = 0, tphase = 0;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
@@ -333,6 +339,13 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
     for (int u = 0; u < 8; ++u) ind[u] = UMMA ? pat[a_loc * 8 + u] : 0u;
     const int tile0 = (int)blockIdx.x * 2 + H, tstride = (int)gridDim.x * 2;
+    // optional phase timeline (debug): CTA 0, first thread of each group of each half, PROF_STAMPS clock stamps per tile
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && (ht & 127) == 0;
+    int prof_seq = 0;
+#define PROF_STAMP(kk)                                                                                          \
+    do {                                                                                                         \
+        if (profiling && prof_seq < prof_tiles) prof[((size_t)prof_seq * 4 + H * 2 + grp) * PROF_STAMPS + (kk)] = clock64(); \
+    } while (0)
     int j_next = 0;
     float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tile0 < n_tiles) {
@@ -341,9 +354,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         g_next = geom[(size_t)i0 * KMAX + k];
         // neighbour factors T_j of the first tile -> shared memory (one 512-byte bulk copy per edge)
         if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
-        if (grp == 0) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
+        if (grp == 1) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
     }
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
+        PROF_STAMP(0);
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
         const int j = j_next;
         const float4 g = g_next;
@@ -351,11 +365,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         const float *sJ = state_in + (size_t)j * SR;
         const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
 
-        float u0v[UMMA ? TA / 2 : 1];
-        if (UMMA) {      // U_i of the tile's atoms (consumed at the end of S0)
+        float u0v[UMMA ? TA : 1];
+        if (UMMA && grp == 1) {      // U_i of the tile's atoms (consumed at the end of S0; group 1 has the lighter S0)
 #pragma unroll
-            for (int m = 0; m < TA / 2; ++m) {
-                const int v = ht + 256 * m;
+            for (int m = 0; m < TA; ++m) {
+                const int v = e + 128 * m;
                 const int ia = min(tile * TA + (v >> 7), n_atoms - 1);
                 u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + (v & 127));
             }
@@ -395,10 +409,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 if (SPLIT) tc::tmem_st8(tlane + TY + 72, ld);
             }
         }
-        if (UMMA) {      // U_i (already scaled by log2 e) as three bf16 planes -> rows 65 + 3 a + p of B1
+        if (UMMA && grp == 1) {      // U_i (already scaled by log2 e) as three bf16 planes -> rows 65 + 3 a + p of B1
 #pragma unroll
-            for (int m = 0; m < TA / 2; ++m) {
-                const int v = ht + 256 * m, a = v >> 7, n = v & 127;
+            for (int m = 0; m < TA; ++m) {
+                const int v = e + 128 * m, a = v >> 7, n = v & 127;
                 const float u0 = u0v[m];
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(u0);
                 const float r1 = u0 - __bfloat162float(h0);
@@ -411,16 +425,18 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     *reinterpret_cast<__nv_bfloat16 *>(ext_hi + (kk >> 3) * 2048 + n * 16 + (kk & 7) * 2) = hp[p];
                 }
             }
-            tc::fence_async_smem();
         }
+        if (UMMA) tc::fence_async_smem();
         tc::wait_st();
         tc::fence_before_sync();
+        PROF_STAMP(1);
         bar_named(bar_id, HALF_THREADS);
-        if (ht == 0) {                                                   // M1: D1 (X) = A1 . B1^T, K = 80
+        PROF_STAMP(2);
+        if (hwarp_u == 0 && tc::elect_one()) {                           // M1: D1 (X) = A1 . B1^T, K = 80
             tc::fence_after_sync();
             const uint32_t idesc = tc::idesc_bf16(128, 128);
             const uint32_t lbo = 128u * 16u;
-#pragma unroll 1
+#pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const uint32_t bh = s < 4 ? img_hi + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_hi_s;
                 const uint64_t dh = tc::smem_desc(bh, lbo, 128u);
@@ -432,13 +448,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                                     tc::smem_desc(img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
                 }
             }
-            tc::umma_commit(bar);
+            tc::umma_commit(bar_u);
         }
         if (alive) alive = tc::mbar_wait(tbar, tphase, &g_tc_watchdog, 4);      // the tile's T_j rows have landed
         tphase ^= 1u;
+        PROF_STAMP(3);
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
         tc::fence_after_sync();
+        PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
 #pragma unroll
@@ -469,17 +487,20 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         }
         tc::wait_st();
         tc::fence_before_sync();
+        PROF_STAMP(5);
         bar_named(bar_id, HALF_THREADS);
-        if (ht == 0) {                                                   // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
+        PROF_STAMP(6);
+        if (hwarp_u == 0 && tc::elect_one()) {                           // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
             tc::fence_after_sync();
-            issue_gemm<SPLIT>(tbase, TY + 0, TX + 0, 16, 2, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q, 32);
-            issue_gemm<SPLIT>(tbase, TY + 32, TX + 32, 16, 2, img_hi + tcimg::B2P, img_lo + tcimg::B2P, 32);
-            issue_gemm<SPLIT>(tbase, TY + 64, TX + 64, 16, 4, img_hi + tcimg::B2V, img_lo + tcimg::B2V, 64);
-            tc::umma_commit(bar);
+            issue_gemm<SPLIT, 2, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
+            issue_gemm<SPLIT, 2, 32>(tbase, TY + 32, TX + 32, 16, img_hi + tcimg::B2P, img_lo + tcimg::B2P);
+            issue_gemm<SPLIT, 4, 64>(tbase, TY + 64, TX + 64, 16, img_hi + tcimg::B2V, img_lo + tcimg::B2V);
+            tc::umma_commit(bar_u);
         }
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 2);
         phase ^= 1u;
         tc::fence_after_sync();
+        PROF_STAMP(7);
 
         // ---------------------------------------------------------------- E2: h2 = ELU(D2 + b2) -> A3 (Y, in place)
 #pragma unroll
@@ -499,13 +520,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         }
         tc::wait_st();
         tc::fence_before_sync();
+        PROF_STAMP(8);
         bar_named(bar_id, HALF_THREADS);
-        if (ht == 0) {                                                   // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
+        PROF_STAMP(9);
+        if (hwarp_u == 0 && tc::elect_one()) {                           // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
             tc::fence_after_sync();
-            issue_gemm<SPLIT>(tbase, TX + 0, TY + 0, 16, 2, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q, 16);
-            issue_gemm<SPLIT>(tbase, TX + 16, TY + 32, 16, 2, img_hi + tcimg::B3P, img_lo + tcimg::B3P, 16);
-            issue_gemm<SPLIT>(tbase, TX + 32, TY + 64, 16, 4, img_hi + tcimg::B3V, img_lo + tcimg::B3V, 64);
-            tc::umma_commit(bar);
+            issue_gemm<SPLIT, 2, 16>(tbase, TX + 0, TY + 0, 16, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q);
+            issue_gemm<SPLIT, 2, 16>(tbase, TX + 16, TY + 32, 16, img_hi + tcimg::B3P, img_lo + tcimg::B3P);
+            issue_gemm<SPLIT, 4, 64>(tbase, TX + 32, TY + 64, 16, img_hi + tcimg::B3V, img_lo + tcimg::B3V);
+            tc::umma_commit(bar_u);
         }
         // neighbour ids of this thread's 8-edge reduction group (phase R), while the tensor core works
         const int pair = ht & 15, rg = ht >> 4;
@@ -529,8 +552,20 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 3);
         phase ^= 1u;
         tc::fence_after_sync();
+        PROF_STAMP(10);
 
         // ---------------------------------------------------------------- E3
+        // p_j of the reduction group's 8 edges (phase R): issued now so that the gather latency overlaps phase E3
+        u64 pjr[8][3];
+        {
+            const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
+#pragma unroll
+            for (int ee = 0; ee < 8; ++ee) {
+                const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
+            }
+        }
         if (grp == 0) {
             // attention weights of this edge (src/model_operations.py:139-140) -> Ws row, every weight duplicated
             // into a pair so that the reduction below can use packed FMAs without register shuffling
@@ -617,19 +652,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         // ---------------------------------------------------------------- R: attention-weighted sums over the edges
         // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
         {
-            // p_j of the group's 8 edges: issued before the barrier so that the gather latency overlaps it
-            u64 pjr[8][3];
-            {
-                const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
-#pragma unroll
-                for (int ee = 0; ee < 8; ++ee) {
-                    const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
-                }
-            }
             tc::fence_before_sync();       // all TMEM reads of this tile are done before the next tile's stores
+            PROF_STAMP(11);
             bar_named(bar_id, HALF_THREADS);
+            PROF_STAMP(12);
             const float *pI = state_in + (size_t)(iaR + 1) * SR + 32 + 2 * pair;
             u64 zq[2], zp[3][2], wi = 0ull;
             zq[0] = zq[1] = 0ull;
@@ -668,6 +694,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 zp[c][0] = fma2(w0, pi, zp[c][0]);
                 zp[c][1] = fma2(w1, pi, zp[c][1]);
             }
+            PROF_STAMP(13);
             bar_named(bar_id, HALF_THREADS);          // every read of Vs is done: the partial sums P alias it
             u64 *P = reinterpret_cast<u64 *>(Vs + rg * 256 + 2 * pair);
             P[0] = zq[0];
@@ -678,6 +705,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 P[48 + 32 * c] = zp[c][1];
             }
             bar_named(bar_id, HALF_THREADS);
+            PROF_STAMP(14);
             // Z record of atom a: [Zq h*32+s | Zp c*64 + h*32 + s]; the per-atom projections qpm / ppm run in the next
             // node kernel, where their weights are reused across 8 atoms
 #pragma unroll
@@ -689,17 +717,24 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
             }
         }
+        PROF_STAMP(15);
         if (tile + tstride < n_tiles) {       // region G is free again: start the bulk copies of the next tile's T_j rows
             bar_named(bar_id, HALF_THREADS);
             tc::fence_async_smem();
             if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
-            if (grp == 0) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
+            if (grp == 1) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
         }
+        PROF_STAMP(16);
+        ++prof_seq;
     }
+#undef PROF_STAMP
     tc::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc::tmem_dealloc(*tmem_slot, TM_COLS);
 }
+
+long long *g_prof_buf = nullptr;      // host-side: device buffer for the debug timeline (nullptr = off)
+int g_prof_tiles = 0;
 
 template <int NN, bool SPLIT>
 int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
@@ -716,7 +751,8 @@ int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const flo
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
     edge_kernel_tc<NN, SPLIT><<<grid, CTA_THREADS, SM_TOTAL, st>>>((const unsigned char *)tcw, n_atoms, ids32,
-                                                                 (const float4 *)geom, state_in, nodeT, nodeC, Zout);
+                                                                 (const float4 *)geom, state_in, nodeT, nodeC, Zout,
+                                                                 g_prof_buf, g_prof_tiles);
     PESTO_CUDA(cudaGetLastError());
     if (getenv("PESTO_TC_DEBUG")) {       // debugging aid: synchronise and report a timed-out tensor-core stage
         PESTO_CUDA(cudaStreamSynchronize(st));
@@ -873,5 +909,16 @@ extern "C" int pesto_debug_umma_probe(const float *A, const float *B, float *D, 
     PESTO_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, split, l, s, id);
     PESTO_CUDA(cudaGetLastError());
+    return PESTO_OK;
+}
+
+/* Debug: while buf != NULL every tensor-core edge-kernel launch records, for CTA 0, clock64() stamps at 17 phase
+ * boundaries per tile into buf[tile_seq][half][group][17] (device memory, int64) for the first max_tiles tiles of
+ * each half.  Stamp order: 0 tile start, 1 S0 done, 2 barrier, 3 T_j landed, 4 M1 done, 5 E1 done, 6 barrier,
+ * 7 M2 done, 8 E2 done, 9 barrier, 10 M3 done, 11 E3 done, 12 barrier, 13 R loop done, 14 partial sums visible,
+ * 15 Z written, 16 next T copies issued. */
+extern "C" int pesto_debug_edge_timeline(void *buf, int max_tiles) {
+    pesto::g_prof_buf = (long long *)buf;
+    pesto::g_prof_tiles = buf ? max_tiles : 0;
     return PESTO_OK;
 }
