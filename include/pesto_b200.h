@@ -148,7 +148,7 @@ int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int 
                            int lbo, int sbo, int idesc, void *stream);
 
 /* Debug: phase timeline of the tensor-core edge kernel.  While buf != NULL, every edge-kernel launch makes CTA 0
- * write clock64() stamps at 17 phase boundaries per tile to buf[tile][half 0..1][column group 0..1][17] (device
+ * write clock64() stamps at 19 phase boundaries per tile to buf[tile][half 0..1][column group 0..1][19] (device
  * int64) for the first max_tiles tiles of each half; buf == NULL switches it off. */
 int pesto_debug_edge_timeline(void *buf, int max_tiles);
 

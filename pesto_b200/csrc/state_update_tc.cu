@@ -119,7 +119,7 @@ constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 
 constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
 constexpr int WS_STRIDE = 28;         // floats per edge row of the attention-weight buffer (112 B: conflict-free STS.128)
-constexpr int PROF_STAMPS = 17;       // clock stamps per tile of the debug timeline (pesto_debug_edge_timeline)
+constexpr int PROF_STAMPS = 19;       // clock stamps per tile of the debug timeline (pesto_debug_edge_timeline)
 constexpr int TS_STRIDE = 132;        // floats per staged T_j row (528 B: conflict-free row-per-lane LDS.128)
 
 // per-half shared memory (byte offsets).  Region G is time-shared inside a tile: the neighbour factors T_j of the
@@ -280,15 +280,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     float *Ws = reinterpret_cast<float *>(hs + HS_WS);
     float *red = reinterpret_cast<float *>(hs + HS_RED);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H;
-    uint64_t *tbar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 2 + H;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 32);
 
     if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
     if (tid == 0) {
         tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR), 1);
         tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 1, 1);
-        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 2, 1);
-        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 3, 1);
         tc::fence_mbar_init();
     }
     for (int u = tid; u < tcimg::TOTAL / 16; u += CTA_THREADS)
@@ -325,7 +322,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const uint32_t ext_hi_s = img_hi + SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI;
     uint64_t *bar_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
-    uint32_t phase = 0, tphase = 0;
+    uint32_t phase = 0;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
     PairConsts kc;
     kc.neg1 = pk2(-1.f, -1.f);
@@ -348,13 +345,23 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     } while (0)
     int j_next = 0;
     float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    // neighbour factors T_j of a tile's 128 edges -> region G, asynchronously (cp.async, 16 B per lane): each warp
+    // copies 16 rows of its own TMEM lane quarter, one 512-byte row per instruction, the row id taken by shuffle
+    // from the lane that owns the edge
+    auto stage_T = [&](int jn) {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int src_lane = grp * 16 + it;
+            const int jr = __shfl_sync(FULLM, jn, src_lane);
+            tc::cp_async16(Ts + (quarter * 32 + src_lane) * TS_STRIDE + lane * 4, nodeT + (size_t)jr * NODE_T_STRIDE + lane * 4);
+        }
+        tc::cp_async_commit();
+    };
     if (tile0 < n_tiles) {
         const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
         j_next = ids32[(size_t)i0 * KMAX + k];
         g_next = geom[(size_t)i0 * KMAX + k];
-        // neighbour factors T_j of the first tile -> shared memory (one 512-byte bulk copy per edge)
-        if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
-        if (grp == 1) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
+        stage_T(j_next);
     }
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
         PROF_STAMP(0);
@@ -427,6 +434,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
         }
         if (UMMA) tc::fence_async_smem();
+        tc::cp_async_wait_all();             // this thread's share of the tile's T_j rows has landed (read in E1)
         tc::wait_st();
         tc::fence_before_sync();
         PROF_STAMP(1);
@@ -450,8 +458,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
             tc::umma_commit(bar_u);
         }
-        if (alive) alive = tc::mbar_wait(tbar, tphase, &g_tc_watchdog, 4);      // the tile's T_j rows have landed
-        tphase ^= 1u;
         PROF_STAMP(3);
         if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
         phase ^= 1u;
@@ -566,6 +572,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
             }
         }
+        PROF_STAMP(17);
         if (grp == 0) {
             // attention weights of this edge (src/model_operations.py:139-140) -> Ws row, every weight duplicated
             // into a pair so that the reduction below can use packed FMAs without register shuffling
@@ -644,6 +651,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 }
             }
         }
+        PROF_STAMP(18);
         if (tile + tstride < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
             const int in = min((tile + tstride) * TA + a_loc, n_atoms - 1);
             j_next = ids32[(size_t)in * KMAX + k];
@@ -718,11 +726,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
         }
         PROF_STAMP(15);
-        if (tile + tstride < n_tiles) {       // region G is free again: start the bulk copies of the next tile's T_j rows
+        if (tile + tstride < n_tiles) {       // region G is free again: start the copies of the next tile's T_j rows
             bar_named(bar_id, HALF_THREADS);
-            tc::fence_async_smem();
-            if (ht == 0) tc::mbar_arrive_expect_tx(tbar, 128u * 512u);
-            if (grp == 1) tc::bulk_g2s(Ts + e * TS_STRIDE, nodeT + (size_t)j_next * NODE_T_STRIDE, 512u, tbar);
+            stage_T(j_next);
         }
         PROF_STAMP(16);
         ++prof_seq;
@@ -914,9 +920,9 @@ extern "C" int pesto_debug_umma_probe(const float *A, const float *B, float *D, 
 
 /* Debug: while buf != NULL every tensor-core edge-kernel launch records, for CTA 0, clock64() stamps at 17 phase
  * boundaries per tile into buf[tile_seq][half][group][17] (device memory, int64) for the first max_tiles tiles of
- * each half.  Stamp order: 0 tile start, 1 S0 done, 2 barrier, 3 T_j landed, 4 M1 done, 5 E1 done, 6 barrier,
+ * each half.  Stamp order: 0 tile start, 1 S0 done, 2 barrier, 3 (unused), 4 M1 done, 5 E1 done, 6 barrier,
  * 7 M2 done, 8 E2 done, 9 barrier, 10 M3 done, 11 E3 done, 12 barrier, 13 R loop done, 14 partial sums visible,
- * 15 Z written, 16 next T copies issued. */
+ * 15 Z written, 16 next T copies issued, 17 p_j prefetch issued (inside E3), 18 E3 arithmetic done. */
 extern "C" int pesto_debug_edge_timeline(void *buf, int max_tiles) {
     pesto::g_prof_buf = (long long *)buf;
     pesto::g_prof_tiles = buf ? max_tiles : 0;

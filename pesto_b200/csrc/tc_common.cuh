@@ -116,6 +116,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// ---- cp.async (LDGSTS): 16 bytes global -> shared per lane, L2 only -------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- UMMA ----------------------------------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major, no swizzle: element (row n, k) of a bf16 operand lives at
 //     base + (k/8)*lbo + (n/8)*sbo + (n%8)*16 + (k%8)*2   bytes

@@ -26,7 +26,7 @@ Xd = X.cuda()
 ids1 = extract_topology(Xd, 64)[0] + 1
 q0, ridd = one_hot_features(el).cuda(), rid.int().cuda()
 lib = _lib.load()
-NS = 17
+NS = 19
 buf = torch.zeros((a.tiles, 2, 2, NS), dtype=torch.int64, device="cuda")
 z = model(Xd, ids1, q0, ridd, n_res=int(rid.max()) + 1)              # warm-up
 lib.pesto_debug_edge_timeline(buf.data_ptr(), a.tiles)
@@ -34,16 +34,20 @@ z = model(Xd, ids1, q0, ridd, n_res=int(rid.max()) + 1)
 torch.cuda.synchronize()
 lib.pesto_debug_edge_timeline(None, 0)
 t = buf.cpu().numpy().astype(np.float64)
-names = ["S0 compute", "barrier A", "wait T_j", "wait M1", "E1 compute", "barrier B", "wait M2", "E2 compute", "barrier C",
+names = ["S0 compute", "barrier A", "(T_j: cp.async, no wait)", "wait M1", "E1 compute", "barrier B", "wait M2", "E2 compute", "barrier C",
          "wait M3", "E3 compute(+pj issue)", "barrier D", "R loop", "barrier E + P", "combine", "barrier G + T issue"]
 valid = t[..., 0] > 0
 n_ok = int(valid.all(axis=(1, 2)).sum())
 t = t[2:n_ok]
+extra = t[..., 17:]
+t = t[..., :17]
 d = np.diff(t, axis=-1)                      # [tiles, half, grp, 16]
 print(f"tiles used: {t.shape[0]}; cycles per tile (mean over tiles), CTA 0")
 print(f"{'phase':28s} " + " ".join(f"H{h}g{gg:1d}".rjust(8) for h in range(2) for gg in range(2)))
 for k, nm in enumerate(names):
     print(f"{nm:28s} " + " ".join(f"{d[:, h, gg, k].mean():8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'  E3: p_j prefetch issue':28s} " + " ".join(f"{(extra[:, h, gg, 0] - t[:, h, gg, 10]).mean():8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'  E3: arithmetic':28s} " + " ".join(f"{(extra[:, h, gg, 1] - extra[:, h, gg, 0]).mean():8.0f}" for h in range(2) for gg in range(2)))
 tot = t[:, :, :, -1] - t[:, :, :, 0]
 print(f"{'tile total':28s} " + " ".join(f"{tot[:, h, gg].mean():8.0f}" for h in range(2) for gg in range(2)))
 per = np.diff(t[:, :, :, 0], axis=0)
