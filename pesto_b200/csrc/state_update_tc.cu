@@ -66,6 +66,10 @@ static inline float bf16_to_f32(uint16_t h) {
     return f;
 }
 
+// K position (0..31) of the p_j.r block of A1 -> state channel: the thread with m = lane % 4 gathers channels 8m..8m+7
+// of its row and owns TMEM columns 2m, 2m+1 (first four channels) and 8+2m, 8+2m+1 (last four) of the 16-column plane
+static inline int pjr_channel(int p) { return p < 16 ? 8 * (p / 4) + p % 4 : 8 * ((p - 16) / 4) + 4 + (p - 16) % 4; }
+
 void pack_tc_layer(const float *blob, void *dst_v) {
     unsigned char *dst = (unsigned char *)dst_v;
     memset(dst, 0, tcimg::TOTAL);
@@ -78,7 +82,8 @@ void pack_tc_layer(const float *blob, void *dst_v) {
     };
     for (int o = 0; o < 128; ++o) {
         for (int s = 0; s < 32; ++s) {
-            put(tcimg::B1, 128, o, s, LOG2E * blob[L::E_WB + s * 128 + o]);          // p_j . r
+            // p_j . r: K position s holds channel pjr_channel(s) (the order in which the gather threads produce them)
+            put(tcimg::B1, 128, o, s, LOG2E * blob[L::E_WB + pjr_channel(s) * 128 + o]);
             put(tcimg::B1, 128, o, 32 + s, LOG2E * blob[L::N_A + s * 128 + o]);      // p_i . r
         }
         put(tcimg::B1, 128, o, 64, LOG2E * blob[L::E_WD + o]);                       // d
@@ -363,13 +368,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         g_next = geom[(size_t)i0 * KMAX + k];
         stage_T(j_next);
     }
+#ifdef PESTO_EXPERIMENT_ONE_HALF
+    if (H == 0)
+#endif
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
         PROF_STAMP(0);
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
         const int j = j_next;
         const float4 g = g_next;
         const float *sI = state_in + (size_t)(i + 1) * SR;
-        const float *sJ = state_in + (size_t)j * SR;
         const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
 
         float u0v[UMMA ? TA : 1];
@@ -384,9 +391,43 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y)
         // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
         // group 0: p_j.r, group 1: p_i.r, d
-        {
-            const float *src = grp == 0 ? sJ : sI;
-            const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
+        const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
+        if (grp == 0) {
+            // p_j . r through the 16x256b store shape: four neighbouring lanes share an edge row and read one 128-byte
+            // line of p_j per component (8 lines per load instruction instead of 32); each thread covers the rows
+            // 8k + lane/4 (k < 4) of its warp's 32 edges and the channels 8m .. 8m+7, m = lane % 4
+            uint32_t hiw[4][4], low[4][4];
+#pragma unroll
+            for (int kr = 0; kr < 4; ++kr) {
+                const int sl = 8 * kr + (lane >> 2);
+                const int jk = __shfl_sync(FULLM, j, sl);
+                const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
+                const u64 kx = pk2(rx, rx), ky = pk2(ry, ry), kz = pk2(rz, rz);
+                const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
+                float x[8], y[8], z[8];
+                tc::ldg256(sJk, x);
+                tc::ldg256(sJk + 32, y);
+                tc::ldg256(sJk + 64, z);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const u64 pr = fma2(kz, pk2(z[2 * u], z[2 * u + 1]), fma2(ky, pk2(y[2 * u], y[2 * u + 1]), mul2(kx, pk2(x[2 * u], x[2 * u + 1]))));
+                    split2<SPLIT>(pr, kc, hiw[kr][u], low[kr][u]);
+                }
+            }
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                const uint32_t ta = tlane + ((uint32_t)(16 * hb) << 16) + TY;
+                const uint32_t h8[8] = {hiw[2 * hb][0], hiw[2 * hb][1], hiw[2 * hb + 1][0], hiw[2 * hb + 1][1],
+                                        hiw[2 * hb][2], hiw[2 * hb][3], hiw[2 * hb + 1][2], hiw[2 * hb + 1][3]};
+                tc::tmem_st_16x256b_x2(ta, h8);
+                if (SPLIT) {
+                    const uint32_t l8[8] = {low[2 * hb][0], low[2 * hb][1], low[2 * hb + 1][0], low[2 * hb + 1][1],
+                                            low[2 * hb][2], low[2 * hb][3], low[2 * hb + 1][2], low[2 * hb + 1][3]};
+                    tc::tmem_st_16x256b_x2(ta + 40, l8);
+                }
+            }
+        } else {
+            const float *src = sI;
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int s = 0; s < S; s += 8) {
@@ -400,9 +441,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     split2<SPLIT>(pr, kc, hi[(s + u) >> 1], lo[(s + u) >> 1]);
                 }
             }
-            tc::tmem_st16(tlane + TY + 16 * grp, hi);
-            if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16 * grp, lo);
-            if (grp == 1) {
+            tc::tmem_st16(tlane + TY + 16, hi);
+            if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16, lo);
+            {
                 uint32_t hd[8], ld[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { hd[u] = ind[u]; ld[u] = 0u; }

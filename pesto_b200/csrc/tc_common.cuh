@@ -76,6 +76,17 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// 16x256b.x2: the warp writes 16 TMEM lanes x 16 columns; thread t supplies, with m = t % 4 and row = t / 4:
+//   r0,r1 -> lane base+row,   columns 2m, 2m+1      r2,r3 -> lane base+8+row, columns 2m, 2m+1
+//   r4,r5 -> lane base+row,   columns 8+2m, 8+2m+1  r6,r7 -> lane base+8+row, columns 8+2m, 8+2m+1
+// (measured with profiles/microbench/tmem_shape.cu); four neighbouring threads share a row, which lets them read
+// one contiguous 128-byte piece of a gathered row
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -37,18 +37,19 @@ t = buf.cpu().numpy().astype(np.float64)
 names = ["S0 compute", "barrier A", "(T_j: cp.async, no wait)", "wait M1", "E1 compute", "barrier B", "wait M2", "E2 compute", "barrier C",
          "wait M3", "E3 compute(+pj issue)", "barrier D", "R loop", "barrier E + P", "combine", "barrier G + T issue"]
 valid = t[..., 0] > 0
-n_ok = int(valid.all(axis=(1, 2)).sum())
+n_ok = int(valid.any(axis=(1, 2)).sum())
 t = t[2:n_ok]
+t[t == 0] = np.nan                              # a half that ran fewer tiles (or was switched off in an experiment)
 extra = t[..., 17:]
 t = t[..., :17]
 d = np.diff(t, axis=-1)                      # [tiles, half, grp, 16]
 print(f"tiles used: {t.shape[0]}; cycles per tile (mean over tiles), CTA 0")
 print(f"{'phase':28s} " + " ".join(f"H{h}g{gg:1d}".rjust(8) for h in range(2) for gg in range(2)))
 for k, nm in enumerate(names):
-    print(f"{nm:28s} " + " ".join(f"{d[:, h, gg, k].mean():8.0f}" for h in range(2) for gg in range(2)))
-print(f"{'  E3: p_j prefetch issue':28s} " + " ".join(f"{(extra[:, h, gg, 0] - t[:, h, gg, 10]).mean():8.0f}" for h in range(2) for gg in range(2)))
-print(f"{'  E3: arithmetic':28s} " + " ".join(f"{(extra[:, h, gg, 1] - extra[:, h, gg, 0]).mean():8.0f}" for h in range(2) for gg in range(2)))
+    print(f"{nm:28s} " + " ".join(f"{np.nanmean(d[:, h, gg, k]):8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'  E3: p_j prefetch issue':28s} " + " ".join(f"{np.nanmean((extra[:, h, gg, 0] - t[:, h, gg, 10])):8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'  E3: arithmetic':28s} " + " ".join(f"{np.nanmean((extra[:, h, gg, 1] - extra[:, h, gg, 0])):8.0f}" for h in range(2) for gg in range(2)))
 tot = t[:, :, :, -1] - t[:, :, :, 0]
-print(f"{'tile total':28s} " + " ".join(f"{tot[:, h, gg].mean():8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'tile total':28s} " + " ".join(f"{np.nanmean(tot[:, h, gg]):8.0f}" for h in range(2) for gg in range(2)))
 per = np.diff(t[:, :, :, 0], axis=0)
-print(f"{'tile period':28s} " + " ".join(f"{per[:, h, gg].mean():8.0f}" for h in range(2) for gg in range(2)))
+print(f"{'tile period':28s} " + " ".join(f"{np.nanmean(per[:, h, gg]):8.0f}" for h in range(2) for gg in range(2)))
