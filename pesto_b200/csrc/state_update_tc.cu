@@ -140,8 +140,8 @@ constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;
 static_assert(HS_WS + 128 * WS_STRIDE * 4 <= HS_RED, "V / weight buffers fit into the T staging region");
 constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
 constexpr int SM_HALF0 = SM_PAT + 128;
-constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // 2 MMA mbarriers, 2 T-copy mbarriers, TMEM slot
-constexpr int SM_TOTAL = SM_BAR + 48;
+constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // per half: 4 MMA chunk mbarriers + 1 T-copy mbarrier; TMEM slot
+constexpr int SM_TOTAL = SM_BAR + 96;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget of one CTA per SM");
 static_assert(SM_HALF0 % 128 == 0 && HS_BYTES % 128 == 0, "per-half regions stay 128-byte aligned");
 
@@ -226,11 +226,12 @@ __device__ __forceinline__ float seg_sum_tc(float v) {
 }
 
 // issue D[d_col .. d_col+N) (+)= A(K columns packed at a_col: hi at +8s, lo at +lo_off+8s per 16-wide K step) . B^T
-template <bool SPLIT, int KSTEPS, int N>
+// N = columns of this MMA, NIMG = rows of the weight image ([K/8][NIMG][8]) the N rows starting at b_hi / b_lo belong to
+template <bool SPLIT, int KSTEPS, int N, int NIMG>
 __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t b_hi,
                                            uint32_t b_lo) {
     constexpr uint32_t idesc = tc::idesc_bf16(128, N);
-    constexpr uint32_t lbo = (uint32_t)N * 16u;
+    constexpr uint32_t lbo = (uint32_t)NIMG * 16u;
 #pragma unroll
     for (int s = 0; s < KSTEPS; ++s) {
         // K steps inside one 32-wide activation chunk are 8 columns apart; chunks are 32 columns apart
@@ -284,13 +285,14 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     float *Vs = reinterpret_cast<float *>(hs + HS_VS);
     float *Ws = reinterpret_cast<float *>(hs + HS_WS);
     float *red = reinterpret_cast<float *>(hs + HS_RED);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 32);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H;     // [0..3]: column chunks, [4]: T_j copies
+    uint64_t *tbar = bars + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 80);
 
     if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
     if (tid == 0) {
-        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR), 1);
-        tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 1, 1);
+        for (int b = 0; b < 10; ++b)
+            tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + b, b % 5 == 4 ? HALF_THREADS : 1);
         tc::fence_mbar_init();
     }
     for (int u = tid; u < tcimg::TOTAL / 16; u += CTA_THREADS)
@@ -325,9 +327,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
     const uint32_t img_hi = tc::smem_u32(smem_raw), img_lo = img_hi + tcimg::IMG;
     const uint32_t ext_hi_s = img_hi + SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI;
-    uint64_t *bar_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + H_u;
+    uint64_t *bars_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
-    uint32_t phase = 0;
+    uint32_t ph0 = 0, ph1 = 0, pht = 0;      // parities of this thread's two chunk barriers (2 grp, 2 grp + 1) and of tbar
+    uint64_t *bar0 = bars + 2 * grp, *bar1 = bar0 + 1;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
     PairConsts kc;
     kc.neg1 = pk2(-1.f, -1.f);
@@ -360,7 +363,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             const int jr = __shfl_sync(FULLM, jn, src_lane);
             tc::cp_async16(Ts + (quarter * 32 + src_lane) * TS_STRIDE + lane * 4, nodeT + (size_t)jr * NODE_T_STRIDE + lane * 4);
         }
-        tc::cp_async_commit();
+        tc::cp_async_mbar_arrive(tbar);
     };
     if (tile0 < n_tiles) {
         const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
@@ -398,21 +401,28 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             // 8k + lane/4 (k < 4) of its warp's 32 edges and the channels 8m .. 8m+7, m = lane % 4
             uint32_t hiw[4][4], low[4][4];
 #pragma unroll
-            for (int kr = 0; kr < 4; ++kr) {
-                const int sl = 8 * kr + (lane >> 2);
-                const int jk = __shfl_sync(FULLM, j, sl);
-                const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
-                const u64 kx = pk2(rx, rx), ky = pk2(ry, ry), kz = pk2(rz, rz);
-                const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
-                float x[8], y[8], z[8];
-                tc::ldg256(sJk, x);
-                tc::ldg256(sJk + 32, y);
-                tc::ldg256(sJk + 64, z);
+            for (int kb = 0; kb < 2; ++kb) {
+                float x[2][8], y[2][8], z[2][8];
+                u64 kx[2], ky[2], kz[2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const u64 pr = fma2(kz, pk2(z[2 * u], z[2 * u + 1]), fma2(ky, pk2(y[2 * u], y[2 * u + 1]), mul2(kx, pk2(x[2 * u], x[2 * u + 1]))));
-                    split2<SPLIT>(pr, kc, hiw[kr][u], low[kr][u]);
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const int sl = 8 * (2 * kb + k2) + (lane >> 2);
+                    const int jk = __shfl_sync(FULLM, j, sl);
+                    const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
+                    kx[k2] = pk2(rx, rx); ky[k2] = pk2(ry, ry); kz[k2] = pk2(rz, rz);
+                    const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
+                    tc::ldg256(sJk, x[k2]);
+                    tc::ldg256(sJk + 32, y[k2]);
+                    tc::ldg256(sJk + 64, z[k2]);
                 }
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const u64 pr = fma2(kz[k2], pk2(z[k2][2 * u], z[k2][2 * u + 1]),
+                                            fma2(ky[k2], pk2(y[k2][2 * u], y[k2][2 * u + 1]), mul2(kx[k2], pk2(x[k2][2 * u], x[k2][2 * u + 1]))));
+                        split2<SPLIT>(pr, kc, hiw[2 * kb + k2][u], low[2 * kb + k2][u]);
+                    }
             }
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
@@ -475,7 +485,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
         }
         if (UMMA) tc::fence_async_smem();
-        tc::cp_async_wait_all();             // this thread's share of the tile's T_j rows has landed (read in E1)
         tc::wait_st();
         tc::fence_before_sync();
         PROF_STAMP(1);
@@ -483,8 +492,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(2);
         if (hwarp_u == 0 && tc::elect_one()) {                           // M1: D1 (X) = A1 . B1^T, K = 80
             tc::fence_after_sync();
-            const uint32_t idesc = tc::idesc_bf16(128, 128);
-            const uint32_t lbo = 128u * 16u;
+            constexpr uint32_t idesc = tc::idesc_bf16(128, 128);
+            constexpr uint32_t lbo = 128u * 16u;
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const uint32_t bh = s < 4 ? img_hi + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_hi_s;
@@ -497,18 +506,21 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                                     tc::smem_desc(img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
                 }
             }
-            tc::umma_commit(bar_u);
+            // (full-width MMAs: N = 32 column chunks with separate commits measured slower at nn = 64)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tc::umma_commit(bars_u + c);
         }
         PROF_STAMP(3);
-        if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 1);
-        phase ^= 1u;
-        tc::fence_after_sync();
+        if (alive) alive = tc::mbar_wait(tbar, pht, &g_tc_watchdog, 4);      // the tile's T_j rows have landed
+        pht ^= 1u;
         PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = 2 * grp + cc;
+            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 1);
+            tc::fence_after_sync();
             uint32_t r[32];
             tc::tmem_ld32(tlane + TX + 32 * c, r);
             u64 y[16];
@@ -539,20 +551,25 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(6);
         if (hwarp_u == 0 && tc::elect_one()) {                           // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
             tc::fence_after_sync();
-            issue_gemm<SPLIT, 2, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
-            issue_gemm<SPLIT, 2, 32>(tbase, TY + 32, TX + 32, 16, img_hi + tcimg::B2P, img_lo + tcimg::B2P);
-            issue_gemm<SPLIT, 4, 64>(tbase, TY + 64, TX + 64, 16, img_hi + tcimg::B2V, img_lo + tcimg::B2V);
-            tc::umma_commit(bar_u);
+            // separate commits: the ELU stage of the first chunks overlaps the remaining MMAs
+            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
+            tc::umma_commit(bars_u + 0);
+            issue_gemm<SPLIT, 4, 64, 64>(tbase, TY + 64, TX + 64, 16, img_hi + tcimg::B2V, img_lo + tcimg::B2V);
+            tc::umma_commit(bars_u + 2);
+            tc::umma_commit(bars_u + 3);
+            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 32, TX + 32, 16, img_hi + tcimg::B2P, img_lo + tcimg::B2P);
+            tc::umma_commit(bars_u + 1);
         }
-        if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 2);
-        phase ^= 1u;
-        tc::fence_after_sync();
+        ph0 ^= 1u;
+        ph1 ^= 1u;
         PROF_STAMP(7);
 
         // ---------------------------------------------------------------- E2: h2 = ELU(D2 + b2) -> A3 (Y, in place)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = 2 * grp + cc;
+            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 2);
+            tc::fence_after_sync();
             uint32_t r[32];
             tc::tmem_ld32(tlane + TY + 32 * c, r);
             tc::wait_ld();
@@ -572,11 +589,16 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(9);
         if (hwarp_u == 0 && tc::elect_one()) {                           // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
             tc::fence_after_sync();
-            issue_gemm<SPLIT, 2, 16>(tbase, TX + 0, TY + 0, 16, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q);
-            issue_gemm<SPLIT, 2, 16>(tbase, TX + 16, TY + 32, 16, img_hi + tcimg::B3P, img_lo + tcimg::B3P);
-            issue_gemm<SPLIT, 4, 64>(tbase, TX + 32, TY + 64, 16, img_hi + tcimg::B3V, img_lo + tcimg::B3V);
-            tc::umma_commit(bar_u);
+            issue_gemm<SPLIT, 2, 16, 16>(tbase, TX + 0, TY + 0, 16, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q);
+            issue_gemm<SPLIT, 2, 16, 16>(tbase, TX + 16, TY + 32, 16, img_hi + tcimg::B3P, img_lo + tcimg::B3P);
+            tc::umma_commit(bars_u + 0);                                 // Kq | Kp: group 0 (attention weights)
+            tc::umma_commit(bars_u + 1);                                 // (keeps three phases per tile on every barrier)
+            issue_gemm<SPLIT, 4, 64, 64>(tbase, TX + 32, TY + 64, 16, img_hi + tcimg::B3V, img_lo + tcimg::B3V);
+            tc::umma_commit(bars_u + 2);                                 // V0 | V1: group 1
+            tc::umma_commit(bars_u + 3);
         }
+        ph0 ^= 1u;
+        ph1 ^= 1u;
         // neighbour ids of this thread's 8-edge reduction group (phase R), while the tensor core works
         const int pair = ht & 15, rg = ht >> 4;
         const int iaR = min(tile * TA + (rg * 8) / NN, n_atoms - 1);
@@ -596,8 +618,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 qv[u] = q4.x; qv[u + 1] = q4.y; qv[u + 2] = q4.z; qv[u + 3] = q4.w;
             }
         }
-        if (alive) alive = tc::mbar_wait(bar, phase, &g_tc_watchdog, 3);
-        phase ^= 1u;
+        if (alive) alive = tc::mbar_wait(bar0, ph0, &g_tc_watchdog, 3);     // group 0: Kq | Kp; group 1: V0
         tc::fence_after_sync();
         PROF_STAMP(10);
 
@@ -678,6 +699,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             // V0 | V1 (+ bias) of this edge -> Vs row
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
+                if (half == 1) {
+                    if (alive) alive = tc::mbar_wait(bar1, ph1, &g_tc_watchdog, 3);
+                    tc::fence_after_sync();
+                }
                 uint32_t r[32];
                 tc::tmem_ld32(tlane + TX + 32 + 32 * half, r);
                 tc::wait_ld();
@@ -692,6 +717,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 }
             }
         }
+        ph0 ^= 1u;      // every chunk barrier completes three times per tile (M1, M2, M3)
+        ph1 ^= 1u;
         PROF_STAMP(18);
         if (tile + tstride < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
             const int in = min((tile + tstride) * TA + a_loc, n_atoms - 1);
