@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -426,12 +427,18 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
     } else if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16) {
         // tensor-core path: the per-atom tail of layer l and the per-atom head of layer l+1 share one launch
         float *Z = w.node + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE);
-        rc = launch_node_fused(nullptr, m->layer(0), cur, nullptr, nullptr, n_atoms, w.node, st);
+        // per-atom kernels: tcgen05 (default) or, with PESTO_NODE=ffma, the FP32-pipe version (A/B checks)
+        static const bool node_ffma = getenv("PESTO_NODE") && !strcmp(getenv("PESTO_NODE"), "ffma");
+        auto node_img = [&](int l) { return (const void *)((const unsigned char *)m->layer_tc(l) + tc_edge_bytes()); };
+        rc = node_ffma ? launch_node_fused(nullptr, m->layer(0), cur, nullptr, nullptr, n_atoms, w.node, st)
+                       : launch_node_umma(nullptr, node_img(0), cur, nullptr, nullptr, n_atoms, w.node, mode, st);
         if (rc != PESTO_OK) return rc;
         for (int l = 0; l < m->n_layers; ++l) {
             rc = launch_edge_tc_layer(m->layer(l), m->layer_tc(l), m->nn[l], n_atoms, w.ids32, w.geom, cur, w.node, Z, mode, st);
             if (rc != PESTO_OK) return rc;
-            rc = launch_node_fused(m->layer(l), l + 1 < m->n_layers ? m->layer(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, st);
+            const bool more = l + 1 < m->n_layers;
+            rc = node_ffma ? launch_node_fused(m->layer(l), more ? m->layer(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, st)
+                           : launch_node_umma(node_img(l), more ? node_img(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, mode, st);
             if (rc != PESTO_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
         }

@@ -134,6 +134,11 @@ int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, 
 int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
                            const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
                            cudaStream_t st, cudaEvent_t *ev);
+int launch_node_umma(const void *img_tail, const void *img_head, const float *state_prev, const float *Z, float *state_new,
+                     int n_atoms, float *node_scratch, int mode, cudaStream_t st);
+size_t node_tc_layer_bytes();
+void pack_node_tc_layer(const float *layer_blob_host, void *dst_host);
+size_t tc_edge_bytes();          // the per-layer image block is [edge images | node images]
 size_t tc_layer_bytes();
 void pack_tc_layer(const float *layer_blob_host, void *dst_host);
 int launch_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, cudaStream_t st);

@@ -50,7 +50,8 @@ constexpr int TOTAL = BIAS + (128 + 96) * 4;
 static_assert(IMG % 16 == 0 && TOTAL % 16 == 0, "images are copied with 16-byte vectors");
 }  // namespace tcimg
 
-size_t tc_layer_bytes() { return tcimg::TOTAL; }
+size_t tc_edge_bytes() { return tcimg::TOTAL; }
+size_t tc_layer_bytes() { return tcimg::TOTAL + node_tc_layer_bytes(); }
 
 static inline uint16_t f32_to_bf16_rne(float f) {
     uint32_t u;
@@ -73,6 +74,7 @@ static inline int pjr_channel(int p) { return p < 16 ? 8 * (p / 4) + p % 4 : 8 *
 void pack_tc_layer(const float *blob, void *dst_v) {
     unsigned char *dst = (unsigned char *)dst_v;
     memset(dst, 0, tcimg::TOTAL);
+    pack_node_tc_layer(blob, dst + tcimg::TOTAL);
     auto put = [&](int img_off, int N, int n, int k, float w) {
         const size_t e = (size_t)(k / 8) * N * 8 + (size_t)n * 8 + (k % 8);
         const uint16_t hi = f32_to_bf16_rne(w);
@@ -879,13 +881,18 @@ int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms
                            const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
                            cudaStream_t st, cudaEvent_t *ev) {
     if (ev) PESTO_CUDA(cudaEventRecord(ev[0], st));
-    int rc = launch_node_fused(nullptr, lw, state_in, nullptr, nullptr, n_atoms, node_scratch, st);
+    const void *nimg = tcw ? (const void *)((const unsigned char *)tcw + tc_edge_bytes()) : nullptr;
+    if (!nimg) {
+        set_error("state_update: tensor-core weight images are missing");
+        return PESTO_ESTATE;
+    }
+    int rc = launch_node_umma(nullptr, nimg, state_in, nullptr, nullptr, n_atoms, node_scratch, mode, st);
     if (rc != PESTO_OK) return rc;
     if (ev) PESTO_CUDA(cudaEventRecord(ev[1], st));
     rc = launch_edge_tc_layer(lw, tcw, nn, n_atoms, ids32, geom, state_in, node_scratch, Z, mode, st);
     if (rc != PESTO_OK) return rc;
     if (ev) PESTO_CUDA(cudaEventRecord(ev[2], st));
-    return launch_node_fused(lw, nullptr, state_in, Z, state_out, n_atoms, node_scratch, st);
+    return launch_node_umma(nimg, nullptr, state_in, Z, state_out, n_atoms, node_scratch, mode, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
