@@ -29,3 +29,40 @@ def test_umma_matches_matmul(K, N):
     # 3-term split: close to the fp32 product
     D3 = probe(A, B, 1)
     assert (D3.double() - ref64).abs().max().item() < 2e-5 * ref64.abs().max().item()
+
+
+def test_edge_timeline_debug_entry():
+    """pesto_debug_edge_timeline: CTA 0 of the tensor-core edge kernel records 19 clock stamps per tile; the first 17
+    are phase boundaries in program order, so they must be non-decreasing, and switching it off must stop the writes."""
+    import json
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from pesto_b200.model import Model
+    from pesto_b200.data_encoding import extract_topology
+    from pesto_b200.synth import synth_structure, one_hot_features
+    lib = _lib.load()
+    with open(os.path.join(GOLDEN, "config_i_v4_0.json")) as fh:
+        model = Model(json.load(fh), mode="bf16x3")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "weights_i_v4_0.npz")).items()})
+    model = model.eval().cuda()
+    X, el, rid = synth_structure(4096, 7)
+    Xd = X.cuda()
+    ids1 = extract_topology(Xd, 64)[0] + 1
+    q0, ridd = one_hot_features(el).cuda(), rid.int().cuda()
+    tiles = 4
+    buf = torch.zeros((tiles, 2, 2, 19), dtype=torch.int64, device="cuda")
+    _lib.check(lib.pesto_debug_edge_timeline(buf.data_ptr(), tiles), "timeline on")
+    with torch.no_grad():
+        z = model(Xd, ids1, q0, ridd, n_res=int(rid.max()) + 1)
+    torch.cuda.synchronize()
+    _lib.check(lib.pesto_debug_edge_timeline(None, 0), "timeline off")
+    t = buf.cpu().numpy()
+    assert (t[..., :17] > 0).all() and torch.isfinite(z).all()
+    assert (np.diff(t[..., :17], axis=-1) >= 0).all()            # program order inside a tile
+    assert (np.diff(t[..., 0], axis=0) > 0).all()                # tiles of one pipeline follow each other
+    buf.zero_()
+    with torch.no_grad():
+        model(Xd, ids1, q0, ridd, n_res=int(rid.max()) + 1)
+    torch.cuda.synchronize()
+    assert int(buf.abs().sum()) == 0
