@@ -179,7 +179,12 @@ def main():
     from pesto_b200.synth import one_hot_features
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner does, from C) are sent
+    # to stderr for the duration of the run, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -333,7 +338,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
