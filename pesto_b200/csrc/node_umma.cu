@@ -134,22 +134,12 @@ __device__ __forceinline__ void nsplit(float a, float b, uint32_t &hi, uint32_t 
     else { hi = tc::pack_bf16x2(a, b); lo = 0u; }
 }
 
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
-}
-
 // fp32 accumulator block (16 columns at taddr, the warp's 32 lanes): v[k][0..3] = row 8k + rl, columns 2m, 2m+1, 8+2m, 9+2m
 __device__ __forceinline__ void load_d16(uint32_t taddr, float (&v)[4][4]) {
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         uint32_t r[8];
-        tmem_ld_16x256b_x2(taddr + ((uint32_t)(16 * hb) << 16), r);
+        tc::tmem_ld_16x256b_x2(taddr + ((uint32_t)(16 * hb) << 16), r);
         tc::wait_ld();
         v[2 * hb][0] = __uint_as_float(r[0]); v[2 * hb][1] = __uint_as_float(r[1]);
         v[2 * hb + 1][0] = __uint_as_float(r[2]); v[2 * hb + 1][1] = __uint_as_float(r[3]);
@@ -163,8 +153,8 @@ __device__ __forceinline__ void store_a8(uint32_t t_hi, uint32_t t_lo, const uin
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const uint32_t lo16 = (uint32_t)(16 * hb) << 16;
-        tmem_st_16x256b_x1(t_hi + lo16, hi[2 * hb][0], hi[2 * hb][1], hi[2 * hb + 1][0], hi[2 * hb + 1][1]);
-        if (SPLIT) tmem_st_16x256b_x1(t_lo + lo16, lo[2 * hb][0], lo[2 * hb][1], lo[2 * hb + 1][0], lo[2 * hb + 1][1]);
+        tc::tmem_st_16x256b_x1(t_hi + lo16, hi[2 * hb][0], hi[2 * hb][1], hi[2 * hb + 1][0], hi[2 * hb + 1][1]);
+        if (SPLIT) tc::tmem_st_16x256b_x1(t_lo + lo16, lo[2 * hb][0], lo[2 * hb][1], lo[2 * hb + 1][0], lo[2 * hb + 1][1]);
     }
 }
 

@@ -71,6 +71,18 @@ static inline float bf16_to_f32(uint16_t h) {
 // of its row and owns TMEM columns 2m, 2m+1 (first four channels) and 8+2m, 8+2m+1 (last four) of the 16-column plane
 static inline int pjr_channel(int p) { return p < 16 ? 8 * (p / 4) + p % 4 : 8 * ((p - 16) / 4) + 4 + (p - 16) % 4; }
 
+// Column (accumulator / operand position 0..31 inside a 32-column chunk) -> channel, for the E-stages' 16x256b register
+// mapping: lane m = lane % 4 owns the columns 2m, 2m+1, 8+2m, 9+2m of each 16-column block and is given the eight
+// consecutive channels 8m .. 8m+7 of the chunk (block 0: 8m..8m+3, block 1: 8m+4..8m+7), so that four lanes read 128
+// contiguous bytes of a gathered T_j row.  The K order this induces on the next GEMM's operand words is pjr_channel.
+__host__ __device__ static inline int chunk_channel(int r) {
+    const int blk = r / 16, q = r % 16;
+    const int m = q < 8 ? q / 2 : (q - 8) / 2, j = q < 8 ? q % 2 : 2 + (q - 8) % 2;
+    return 8 * m + 4 * blk + j;
+}
+__host__ __device__ static inline int col_channel(int c) { return 32 * (c / 32) + chunk_channel(c % 32); }     // any number of 32-column chunks
+static inline int kpos_channel(int p) { return 32 * (p / 32) + pjr_channel(p % 32); }
+
 void pack_tc_layer(const float *blob, void *dst_v) {
     unsigned char *dst = (unsigned char *)dst_v;
     memset(dst, 0, tcimg::TOTAL);
@@ -82,27 +94,28 @@ void pack_tc_layer(const float *blob, void *dst_v) {
         ((uint16_t *)(dst + img_off))[e] = hi;
         ((uint16_t *)(dst + tcimg::IMG + img_off))[e] = lo;
     };
-    for (int o = 0; o < 128; ++o) {
+    for (int n = 0; n < 128; ++n) {                    // first layer: accumulator column n holds channel col_channel(n)
+        const int o = col_channel(n);
         for (int s = 0; s < 32; ++s) {
             // p_j . r: K position s holds channel pjr_channel(s) (the order in which the gather threads produce them)
-            put(tcimg::B1, 128, o, s, LOG2E * blob[L::E_WB + pjr_channel(s) * 128 + o]);
-            put(tcimg::B1, 128, o, 32 + s, LOG2E * blob[L::N_A + s * 128 + o]);      // p_i . r
+            put(tcimg::B1, 128, n, s, LOG2E * blob[L::E_WB + pjr_channel(s) * 128 + o]);
+            put(tcimg::B1, 128, n, 32 + s, LOG2E * blob[L::N_A + s * 128 + o]);      // p_i . r
         }
-        put(tcimg::B1, 128, o, 64, LOG2E * blob[L::E_WD + o]);                       // d
+        put(tcimg::B1, 128, n, 64, LOG2E * blob[L::E_WD + o]);                       // d
     }
     for (int n = 0; n < 32; ++n)
-        for (int k = 0; k < 32; ++k) {
-            put(tcimg::B2Q, 32, n, k, blob[L::E_2Q + k * 32 + n]);
-            put(tcimg::B2P, 32, n, k, blob[L::E_2P + k * 32 + n]);
-            if (n < 3) put(tcimg::B3Q, 16, n, k, ILOG2E * blob[L::E_3Q + k * 4 + n]);
-            if (n < 9) put(tcimg::B3P, 16, n, k, ILOG2E * blob[L::E_3P + k * 12 + n]);
+        for (int k = 0; k < 32; ++k) {                 // second / third layer of eqkm, epkm: operand K position k, column n
+            put(tcimg::B2Q, 32, n, k, blob[L::E_2Q + kpos_channel(k) * 32 + col_channel(n)]);
+            put(tcimg::B2P, 32, n, k, blob[L::E_2P + kpos_channel(k) * 32 + col_channel(n)]);
+            if (n < 3) put(tcimg::B3Q, 16, n, k, ILOG2E * blob[L::E_3Q + kpos_channel(k) * 4 + n]);
+            if (n < 9) put(tcimg::B3P, 16, n, k, ILOG2E * blob[L::E_3P + kpos_channel(k) * 12 + n]);
         }
     for (int n = 0; n < 64; ++n)
         for (int k = 0; k < 64; ++k) {
-            put(tcimg::B2V, 64, n, k, blob[L::E_2V + k * 64 + n]);
-            put(tcimg::B3V, 64, n, k, ILOG2E * blob[L::E_3V + k * 64 + n]);
+            put(tcimg::B2V, 64, n, k, blob[L::E_2V + kpos_channel(k) * 64 + col_channel(n)]);
+            put(tcimg::B3V, 64, n, k, ILOG2E * blob[L::E_3V + kpos_channel(k) * 64 + n]);
         }
-    float *bias = (float *)(dst + tcimg::BIAS);
+    float *bias = (float *)(dst + tcimg::BIAS);        // natural channel order (threads index them by channel)
     for (int i = 0; i < 32; ++i) {
         bias[i] = LOG2E * blob[L::E_2QB + i];
         bias[32 + i] = LOG2E * blob[L::E_2PB + i];
@@ -127,22 +140,16 @@ constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
 constexpr int WS_STRIDE = 28;         // floats per edge row of the attention-weight buffer (112 B: conflict-free STS.128)
 constexpr int PROF_STAMPS = 19;       // clock stamps per tile of the debug timeline (pesto_debug_edge_timeline)
-constexpr int TS_STRIDE = 132;        // floats per staged T_j row (528 B: conflict-free row-per-lane LDS.128)
 
-// per-half shared memory (byte offsets).  Region G is time-shared inside a tile: the neighbour factors T_j of the
-// tile's 128 edges (bulk-copied while the previous stages run, read in E1), then V0|V1 and the attention weights
-// (written in E3, read in R), then the partial sums P of R.
+// per-half shared memory (byte offsets)
 constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64..79: W_d (hi), U planes per tile, W_d (lo)
-constexpr int HS_G = HS_EXT_HI + 4096;
-constexpr int HS_TS = HS_G;                                   // [128][TS_STRIDE] fp32
-constexpr int HS_VS = HS_G;                                   // [128][VS_STRIDE] fp32; aliased by the partial sums P
-constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [128][WS_STRIDE] fp32
-constexpr int HS_RED = HS_G + 128 * TS_STRIDE * 4;            // [4 quarters][8] softmax exchange (nn = 64)
+constexpr int HS_VS = HS_EXT_HI + 4096;                       // [128][VS_STRIDE] fp32 (E3 -> R); aliased by the partial sums P
+constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [128][WS_STRIDE] fp32 attention weights (E3 -> R)
+constexpr int HS_RED = HS_WS + 128 * WS_STRIDE * 4;           // [4 quarters][8] softmax exchange (nn = 64)
 constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;
-static_assert(HS_WS + 128 * WS_STRIDE * 4 <= HS_RED, "V / weight buffers fit into the T staging region");
 constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
 constexpr int SM_HALF0 = SM_PAT + 128;
-constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // per half: 4 MMA chunk mbarriers + 1 T-copy mbarrier; TMEM slot
+constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // per half: 4 MMA chunk mbarriers (+ 1 spare); TMEM slot
 constexpr int SM_TOTAL = SM_BAR + 96;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget of one CTA per SM");
 static_assert(SM_HALF0 % 128 == 0 && HS_BYTES % 128 == 0, "per-half regions stay 128-byte aligned");
@@ -248,14 +255,43 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
     }
 }
 
-// ELU + bf16 (hi|lo) packing of 16 packed pairs -> 32 TMEM columns: [0,16) hi pairs, [16,32) lo pairs
+// E-stage tail in the 16x256b register mapping: y (the addends of this thread's 4 rows x 8 channels of a 32-column
+// chunk) += accumulator; ELU; bf16 hi | lo words stored in place over the chunk: [0,16) hi words, [16,32) lo words.
+// Thread (rl = lane / 4, m = lane % 4): rows 8 k + rl; block bk, word w <-> columns 16 bk + {2m, 2m+1} (w = 0) and
+// 16 bk + {8+2m, 9+2m} (w = 1); as operand words they go to word columns 8 bk + 2m + w (K order pjr_channel).
 template <bool SPLIT>
-__device__ __forceinline__ void activate_store(uint32_t taddr, const u64 (&y)[16], const PairConsts &k) {
-    uint32_t hi[16], lo[16];
+__device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2], const PairConsts &k) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) split2<SPLIT>(elu2_scaled(y[u], k), k, hi[u], lo[u]);
-    tc::tmem_st16(taddr, hi);
-    if (SPLIT) tc::tmem_st16(taddr + 16, lo);
+    for (int bk = 0; bk < 2; ++bk)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            uint32_t r[8];
+            tc::tmem_ld_16x256b_x2(tchunk + 16 * bk + ((uint32_t)(16 * hb) << 16), r);
+            tc::wait_ld();
+            y[bk][2 * hb][0] = add2(y[bk][2 * hb][0], pk2u(r[0], r[1]));
+            y[bk][2 * hb + 1][0] = add2(y[bk][2 * hb + 1][0], pk2u(r[2], r[3]));
+            y[bk][2 * hb][1] = add2(y[bk][2 * hb][1], pk2u(r[4], r[5]));
+            y[bk][2 * hb + 1][1] = add2(y[bk][2 * hb + 1][1], pk2u(r[6], r[7]));
+        }
+    uint32_t hi[2][4][2], lo[2][4][2];
+#pragma unroll
+    for (int bk = 0; bk < 2; ++bk)
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr)
+#pragma unroll
+            for (int w = 0; w < 2; ++w) split2<SPLIT>(elu2_scaled(y[bk][kr][w], k), k, hi[bk][kr][w], lo[bk][kr][w]);
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        const uint32_t ta = tchunk + ((uint32_t)(16 * hb) << 16);
+        const uint32_t h8[8] = {hi[0][2 * hb][0], hi[0][2 * hb][1], hi[0][2 * hb + 1][0], hi[0][2 * hb + 1][1],
+                                hi[1][2 * hb][0], hi[1][2 * hb][1], hi[1][2 * hb + 1][0], hi[1][2 * hb + 1][1]};
+        tc::tmem_st_16x256b_x2(ta, h8);
+        if (SPLIT) {
+            const uint32_t l8[8] = {lo[0][2 * hb][0], lo[0][2 * hb][1], lo[0][2 * hb + 1][0], lo[0][2 * hb + 1][1],
+                                    lo[1][2 * hb][0], lo[1][2 * hb][1], lo[1][2 * hb + 1][0], lo[1][2 * hb + 1][1]};
+            tc::tmem_st_16x256b_x2(ta + 16, l8);
+        }
+    }
 }
 
 // One CTA per SM, 512 threads = two independent 256-thread tile pipelines ("halves") that share the weight images
@@ -283,12 +319,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int grp = hwarp >> 2, quarter = hwarp & 3;       // column group, TMEM lane quarter
     unsigned char *hs = smem_raw + SM_HALF0 + H * HS_BYTES;
     unsigned char *ext_hi = hs + HS_EXT_HI;
-    float *Ts = reinterpret_cast<float *>(hs + HS_TS);
     float *Vs = reinterpret_cast<float *>(hs + HS_VS);
     float *Ws = reinterpret_cast<float *>(hs + HS_WS);
     float *red = reinterpret_cast<float *>(hs + HS_RED);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H;     // [0..3]: column chunks, [4]: T_j copies
-    uint64_t *tbar = bars + 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H;     // [0..3]: column chunks
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 80);
 
     if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -331,7 +365,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const uint32_t ext_hi_s = img_hi + SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI;
     uint64_t *bars_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
-    uint32_t ph0 = 0, ph1 = 0, pht = 0;      // parities of this thread's two chunk barriers (2 grp, 2 grp + 1) and of tbar
+    uint32_t ph0 = 0, ph1 = 0;               // parities of this thread's two chunk barriers (2 grp, 2 grp + 1)
     uint64_t *bar0 = bars + 2 * grp, *bar1 = bar0 + 1;
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
     PairConsts kc;
@@ -355,23 +389,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     } while (0)
     int j_next = 0;
     float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    // neighbour factors T_j of a tile's 128 edges -> region G, asynchronously (cp.async, 16 B per lane): each warp
-    // copies 16 rows of its own TMEM lane quarter, one 512-byte row per instruction, the row id taken by shuffle
-    // from the lane that owns the edge
-    auto stage_T = [&](int jn) {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int src_lane = grp * 16 + it;
-            const int jr = __shfl_sync(FULLM, jn, src_lane);
-            tc::cp_async16(Ts + (quarter * 32 + src_lane) * TS_STRIDE + lane * 4, nodeT + (size_t)jr * NODE_T_STRIDE + lane * 4);
-        }
-        tc::cp_async_mbar_arrive(tbar);
-    };
     if (tile0 < n_tiles) {
         const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
         j_next = ids32[(size_t)i0 * KMAX + k];
         g_next = geom[(size_t)i0 * KMAX + k];
-        stage_T(j_next);
     }
 #ifdef PESTO_EXPERIMENT_ONE_HALF
     if (H == 0)
@@ -390,7 +411,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int m = 0; m < TA; ++m) {
                 const int v = e + 128 * m;
                 const int ia = min(tile * TA + (v >> 7), n_atoms - 1);
-                u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + (v & 127));
+                u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + col_channel(v & 127));    // column n holds channel col_channel(n)
             }
         }
         // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y)
@@ -513,38 +534,50 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int c = 0; c < 4; ++c) tc::umma_commit(bars_u + c);
         }
         PROF_STAMP(3);
-        if (alive) alive = tc::mbar_wait(tbar, pht, &g_tc_watchdog, 4);      // the tile's T_j rows have landed
-        pht ^= 1u;
+        // E-stage register mapping (16x256b): this thread owns the rows 8 k + rl (k < 4) of its warp's 32 edges and, in a
+        // 32-column chunk c, the channels 32 c + 8 m4 .. + 7.  T_j of those rows and channels: one 32-byte load per row
+        // and chunk, four lanes reading one 128-byte line; first chunk prefetched while the tensor core works
+        const int m4 = lane & 3, rl = lane >> 2;
+        int jrow[4];
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr) jrow[kr] = __shfl_sync(FULLM, j, 8 * kr + rl);
+        float tv[4][8];
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr) tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 64 * grp + 8 * m4, tv[kr]);
         PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = 2 * grp + cc;
-            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 1);
-            tc::fence_after_sync();
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TX + 32 * c, r);
-            u64 y[16];
+            u64 y[2][4][2];                                  // [16-column block][row][word = channel pair]
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const ulonglong2 t2 = *reinterpret_cast<const ulonglong2 *>(Ts + e * TS_STRIDE + 32 * c + 4 * u);
-                y[2 * u] = t2.x;
-                y[2 * u + 1] = t2.y;
+            for (int bk = 0; bk < 2; ++bk)
+#pragma unroll
+                for (int kr = 0; kr < 4; ++kr) {
+                    y[bk][kr][0] = pk2(tv[kr][4 * bk], tv[kr][4 * bk + 1]);
+                    y[bk][kr][1] = pk2(tv[kr][4 * bk + 2], tv[kr][4 * bk + 3]);
+                }
+            if (cc == 0) {
+#pragma unroll
+                for (int kr = 0; kr < 4; ++kr) tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 32 * (c + 1) + 8 * m4, tv[kr]);
             }
-            if (!UMMA) {
+            if (!UMMA) {                                     // U_i of the row's atom (nn <= 16: not folded into the MMA)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int kr = 0; kr < 4; ++kr) {
+                    const int ik = min(tile * TA + (quarter * 32 + 8 * kr + rl) / NN, n_atoms - 1);
                     float pu[8];
-                    tc::ldg256(cI + 32 * c + 8 * u, pu);
+                    tc::ldg256(nodeC + (size_t)(ik + 1) * NODE_C_STRIDE + 32 * c + 8 * m4, pu);
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) y[4 * u + w] = add2(y[4 * u + w], pk2(pu[2 * w], pu[2 * w + 1]));
+                    for (int bk = 0; bk < 2; ++bk) {
+                        y[bk][kr][0] = add2(y[bk][kr][0], pk2(pu[4 * bk], pu[4 * bk + 1]));
+                        y[bk][kr][1] = add2(y[bk][kr][1], pk2(pu[4 * bk + 2], pu[4 * bk + 3]));
+                    }
                 }
             }
-            tc::wait_ld();
-#pragma unroll
-            for (int u = 0; u < 16; ++u) y[u] = add2(y[u], pk2u(r[2 * u], r[2 * u + 1]));
-            activate_store<SPLIT>(tlane + TX + 32 * c, y, kc);
+            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 1);
+            tc::fence_after_sync();
+            estage_finish<SPLIT>(tlane + TX + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();
@@ -570,19 +603,16 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const int c = 2 * grp + cc;
+            u64 y[2][4][2];
+#pragma unroll
+            for (int bk = 0; bk < 2; ++bk) {
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b2 + 32 * c + 8 * m4 + 4 * bk);
+#pragma unroll
+                for (int kr = 0; kr < 4; ++kr) { y[bk][kr][0] = bb.x; y[bk][kr][1] = bb.y; }
+            }
             if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 2);
             tc::fence_after_sync();
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TY + 32 * c, r);
-            tc::wait_ld();
-            u64 y[16];
-#pragma unroll
-            for (int u = 0; u < 16; u += 2) {
-                const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b2 + 32 * c + 2 * u);
-                y[u] = add2(pk2u(r[2 * u], r[2 * u + 1]), bb.x);
-                y[u + 1] = add2(pk2u(r[2 * u + 2], r[2 * u + 3]), bb.y);
-            }
-            activate_store<SPLIT>(tlane + TY + 32 * c, y, kc);
+            estage_finish<SPLIT>(tlane + TY + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();
@@ -796,10 +826,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
         }
         PROF_STAMP(15);
-        if (tile + tstride < n_tiles) {       // region G is free again: start the copies of the next tile's T_j rows
-            bar_named(bar_id, HALF_THREADS);
-            stage_T(j_next);
-        }
+
         PROF_STAMP(16);
         ++prof_seq;
     }
