@@ -541,9 +541,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         int jrow[4];
 #pragma unroll
         for (int kr = 0; kr < 4; ++kr) jrow[kr] = __shfl_sync(FULLM, j, 8 * kr + rl);
-        float tv[4][8];
+        float tv[2][4][8];
 #pragma unroll
-        for (int kr = 0; kr < 4; ++kr) tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 64 * grp + 8 * m4, tv[kr]);
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int kr = 0; kr < 4; ++kr)
+                tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 64 * grp + 32 * cc + 8 * m4, tv[cc][kr]);
         PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
@@ -555,13 +558,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int bk = 0; bk < 2; ++bk)
 #pragma unroll
                 for (int kr = 0; kr < 4; ++kr) {
-                    y[bk][kr][0] = pk2(tv[kr][4 * bk], tv[kr][4 * bk + 1]);
-                    y[bk][kr][1] = pk2(tv[kr][4 * bk + 2], tv[kr][4 * bk + 3]);
+                    y[bk][kr][0] = pk2(tv[cc][kr][4 * bk], tv[cc][kr][4 * bk + 1]);
+                    y[bk][kr][1] = pk2(tv[cc][kr][4 * bk + 2], tv[cc][kr][4 * bk + 3]);
                 }
-            if (cc == 0) {
-#pragma unroll
-                for (int kr = 0; kr < 4; ++kr) tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 32 * (c + 1) + 8 * m4, tv[kr]);
-            }
             if (!UMMA) {                                     // U_i of the row's atom (nn <= 16: not folded into the MMA)
 #pragma unroll
                 for (int kr = 0; kr < 4; ++kr) {
@@ -587,11 +586,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (hwarp_u == 0 && tc::elect_one()) {                           // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
             tc::fence_after_sync();
             // separate commits: the ELU stage of the first chunks overlaps the remaining MMAs
-            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
-            tc::umma_commit(bars_u + 0);
             issue_gemm<SPLIT, 4, 64, 64>(tbase, TY + 64, TX + 64, 16, img_hi + tcimg::B2V, img_lo + tcimg::B2V);
             tc::umma_commit(bars_u + 2);
             tc::umma_commit(bars_u + 3);
+            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
+            tc::umma_commit(bars_u + 0);
             issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 32, TX + 32, 16, img_hi + tcimg::B2P, img_lo + tcimg::B2P);
             tc::umma_commit(bars_u + 1);
         }
