@@ -387,24 +387,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     do {                                                                                                         \
         if (profiling && prof_seq < prof_tiles) prof[((size_t)prof_seq * 4 + H * 2 + grp) * PROF_STAMPS + (kk)] = clock64(); \
     } while (0)
-    int j_next = 0;
-    float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tile0 < n_tiles) {
-        const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
-        j_next = ids32[(size_t)i0 * KMAX + k];
-        g_next = geom[(size_t)i0 * KMAX + k];
-    }
-#ifdef PESTO_EXPERIMENT_ONE_HALF
-    if (H == 0)
-#endif
-    for (int tile = tile0; tile < n_tiles; tile += tstride) {
-        PROF_STAMP(0);
-        const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
-        const int j = j_next;
-        const float4 g = g_next;
-        const float *sI = state_in + (size_t)(i + 1) * SR;
-        const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
-
+    // S0 of one tile: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y), U planes -> B1's spare K rows.  It runs one tile AHEAD
+    // (after E3 of the previous tile, when Y is free again), so that the first-layer MMA of a tile executes while
+    // the reduction phase R of the previous tile occupies the CUDA cores.
+    auto stage0 = [&](int tile, int j, const float4 &g) {
+        const float *sI = state_in + (size_t)(min(tile * TA + a_loc, n_atoms - 1) + 1) * SR;
         float u0v[UMMA ? TA : 1];
         if (UMMA && grp == 1) {      // U_i of the tile's atoms (consumed at the end of S0; group 1 has the lighter S0)
 #pragma unroll
@@ -510,9 +497,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (UMMA) tc::fence_async_smem();
         tc::wait_st();
         tc::fence_before_sync();
-        PROF_STAMP(1);
-        bar_named(bar_id, HALF_THREADS);
-        PROF_STAMP(2);
+    };
+    auto issue_m1 = [&]() {
         if (hwarp_u == 0 && tc::elect_one()) {                           // M1: D1 (X) = A1 . B1^T, K = 80
             tc::fence_after_sync();
             constexpr uint32_t idesc = tc::idesc_bf16(128, 128);
@@ -533,6 +519,41 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int c = 0; c < 4; ++c) tc::umma_commit(bars_u + c);
         }
+    };
+    int j_next = 0;
+    float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tile0 < n_tiles) {
+        const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
+        j_next = ids32[(size_t)i0 * KMAX + k];
+        g_next = geom[(size_t)i0 * KMAX + k];
+#ifdef PESTO_EXPERIMENT_ONE_HALF
+        if (H == 0)
+#endif
+        {
+            stage0(tile0, j_next, g_next);
+            bar_named(bar_id, HALF_THREADS);
+            issue_m1();
+        }
+    }
+#ifdef PESTO_EXPERIMENT_ONE_HALF
+    if (H == 0)
+#endif
+    for (int tile = tile0; tile < n_tiles; tile += tstride) {
+        PROF_STAMP(0);
+        const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
+        const int j = j_next;
+        const float4 g = g_next;
+        const float *cI = nodeC + (size_t)(i + 1) * NODE_C_STRIDE;
+        const bool more = tile + tstride < n_tiles;
+        int jn = 0;                                                // the next tile's edge slot (S0 of that tile runs after E3)
+        float4 gn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (more) {
+            const int in = min((tile + tstride) * TA + a_loc, n_atoms - 1);
+            jn = ids32[(size_t)in * KMAX + k];
+            gn = geom[(size_t)in * KMAX + k];
+        }
+        PROF_STAMP(1);
+        PROF_STAMP(2);
         PROF_STAMP(3);
         // E-stage register mapping (16x256b): this thread owns the rows 8 k + rl (k < 4) of its warp's 32 edges and, in a
         // 32-column chunk c, the channels 32 c + 8 m4 .. + 7.  T_j of those rows and channels: one 32-byte load per row
@@ -654,17 +675,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(10);
 
         // ---------------------------------------------------------------- E3
-        // p_j of the reduction group's 8 edges (phase R): issued now so that the gather latency overlaps phase E3
-        u64 pjr[8][3];
-        {
-            const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
-#pragma unroll
-            for (int ee = 0; ee < 8; ++ee) {
-                const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
-            }
-        }
         PROF_STAMP(17);
         if (grp == 0) {
             // attention weights of this edge (src/model_operations.py:139-140) -> Ws row, every weight duplicated
@@ -751,10 +761,21 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         ph0 ^= 1u;      // every chunk barrier completes three times per tile (M1, M2, M3)
         ph1 ^= 1u;
         PROF_STAMP(18);
-        if (tile + tstride < n_tiles) {       // next tile's edge slot: hide the index -> gather dependency
-            const int in = min((tile + tstride) * TA + a_loc, n_atoms - 1);
-            j_next = ids32[(size_t)in * KMAX + k];
-            g_next = geom[(size_t)in * KMAX + k];
+        if (more) {
+            if (grp == 0 && alive) alive = tc::mbar_wait(bars + 3, ph1 ^ 1u, &g_tc_watchdog, 3);   // every MMA of M3 has read Y
+            tc::fence_after_sync();
+            stage0(tile + tstride, jn, gn);
+        }
+        // p_j of the reduction group's 8 edges (phase R): issued before the barrier so that part of the gather latency overlaps it
+        u64 pjr[8][3];
+        {
+            const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
+#pragma unroll
+            for (int ee = 0; ee < 8; ++ee) {
+                const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
+            }
         }
         // ---------------------------------------------------------------- R: attention-weighted sums over the edges
         // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
@@ -763,6 +784,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             PROF_STAMP(11);
             bar_named(bar_id, HALF_THREADS);
             PROF_STAMP(12);
+            if (more) issue_m1();          // the next tile's first-layer MMA runs underneath this tile's reduction
             const float *pI = state_in + (size_t)(iaR + 1) * SR + 32 + 2 * pair;
             u64 zq[2], zp[3][2], wi = 0ull;
             zq[0] = zq[1] = 0ull;
@@ -828,6 +850,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 
         PROF_STAMP(16);
         ++prof_seq;
+        j_next = jn;
+        g_next = gn;
     }
 #undef PROF_STAMP
     tc::fence_before_sync();
