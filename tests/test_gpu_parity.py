@@ -386,3 +386,43 @@ def test_logits_bf16_speed_mode_reports_its_error(cuda_models):
     perr = (torch.sigmoid(z) - torch.sigmoid(ref)).abs().max().item()
     print(f"bf16 speed mode: max|dz| = {err:.3e}, max|dp| = {perr:.3e}")
     assert err < 1.0 and perr < 0.1
+
+
+def test_config4_large_chain_32768(cuda_models):
+    """BASELINE config 4 (one N = 32 768 chain, i_v4_1): too large for the CPU oracle in test time, so checked through
+    size-independent properties: finite logits, rigid-motion invariance, and agreement with the fp32 (FFMA) path."""
+    from pesto_b200.data_encoding import extract_topology
+    X, el, rid = synth_structure(32768, BASE_SEED + 4)
+    Xd, q0, ridd = X.cuda(), one_hot_features(el).cuda(), rid.int().cuda()
+    ids0 = extract_topology(Xd, 64)[0]
+    assert ids0.shape == (32768, 64) and int(ids0.min()) >= 0 and int(ids0.max()) < 32768
+    ids1 = ids0 + 1
+    model = cuda_models("i_v4_1")
+    z = model(Xd, ids1, q0, ridd, n_res=4096)
+    assert z.shape == (4096, 5) and torch.isfinite(z).all()
+    g = torch.Generator().manual_seed(4)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    X2 = (X.double() @ Q + torch.tensor([-3.0, 100.0, 55.5], dtype=torch.float64)).float().cuda()
+    assert (z - model(X2, ids1, q0, ridd, n_res=4096)).abs().max().item() <= 2e-3
+    z32 = model(Xd, ids1, q0, ridd, n_res=4096, mode="fp32")
+    assert (z - z32).abs().max().item() <= LOGIT_TOL
+
+
+def test_config3_batch_of_8192_atom_structures(cuda_models):
+    """BASELINE config 3 (i_v4_0, synthetic N = 8192 structures collated into one batch): the batched forward over
+    several structures equals the separate forwards (the full 32-structure batch is timed by profiles/bench_configs.py)."""
+    from pesto_b200.data_encoding import batch_topology, extract_topology
+    model = cuda_models("i_v4_0")
+    n, n_struct = 8192, 4
+    Xs, els, rids = zip(*[synth_structure(n, BASE_SEED + 100 + s) for s in range(n_struct)])
+    Xb = torch.cat(Xs).cuda()
+    q0b = one_hot_features(torch.cat(els)).cuda()
+    ridb = torch.cat([r + s * (n // 8) for s, r in enumerate(rids)]).int().cuda()
+    ids1b = batch_topology(Xb, [n] * n_struct, 64)
+    zb = model(Xb, ids1b, q0b, ridb, n_res=n_struct * (n // 8))
+    for s in (0, n_struct - 1):
+        Xd = Xs[s].cuda()
+        ids1 = extract_topology(Xd, 64)[0] + 1
+        assert torch.equal(ids1b[s * n:(s + 1) * n] - s * n, ids1)          # 1-based global ids of collate_batch_features
+        zs = model(Xd, ids1, one_hot_features(els[s]).cuda(), rids[s].int().cuda(), n_res=n // 8)
+        assert (zb[s * (n // 8):(s + 1) * (n // 8)] - zs).abs().max().item() <= 1e-4
