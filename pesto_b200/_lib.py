@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpesto_b200.so")
+# PESTO_B200_LIB: experiment aid (profiles/variants.py builds kernel variants side by side); the default is the in-tree build
+LIB_PATH = os.environ.get("PESTO_B200_LIB") or os.path.join(_HERE, "libpesto_b200.so")
 
 MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}

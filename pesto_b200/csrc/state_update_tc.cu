@@ -235,10 +235,10 @@ __device__ __forceinline__ float seg_sum_tc(float v) {
 }
 
 // issue D[d_col .. d_col+N) (+)= A(K columns packed at a_col: hi at +8s, lo at +lo_off+8s per 16-wide K step) . B^T
-// N = columns of this MMA, NIMG = rows of the weight image ([K/8][NIMG][8]) the N rows starting at b_hi / b_lo belong to
-template <bool SPLIT, int KSTEPS, int N, int NIMG>
-__device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t b_hi,
-                                           uint32_t b_lo) {
+// N = columns of this MMA, NIMG = rows of the weight image ([K/8][NIMG][8]) the N rows belong to; the image's hi plane
+// starts B_OFF bytes after the shared-memory base (base14 = base address >> 4), its lo plane tcimg::IMG bytes later
+template <bool SPLIT, int KSTEPS, int N, int NIMG, uint32_t B_OFF>
+__device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t base14) {
     constexpr uint32_t idesc = tc::idesc_bf16(128, N);
     constexpr uint32_t lbo = (uint32_t)NIMG * 16u;
 #pragma unroll
@@ -246,11 +246,11 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
         // K steps inside one 32-wide activation chunk are 8 columns apart; chunks are 32 columns apart
         const uint32_t a = tbase + a_col + (uint32_t)(s >> 1) * 32u + (uint32_t)(s & 1) * 8u;
         const uint32_t koff = (uint32_t)s * 2u * lbo;
-        const uint64_t dh = tc::smem_desc(b_hi + koff, lbo, 128u);
+        const uint64_t dh = tc::smem_desc14(base14, B_OFF + koff, lbo, 128u);
         tc::umma_ts(tbase + d_col, a, dh, idesc, s > 0);
         if (SPLIT) {
             tc::umma_ts(tbase + d_col, a + lo_off, dh, idesc, 1u);
-            tc::umma_ts(tbase + d_col, a, tc::smem_desc(b_lo + koff, lbo, 128u), idesc, 1u);
+            tc::umma_ts(tbase + d_col, a, tc::smem_desc14(base14, B_OFF + tcimg::IMG + koff, lbo, 128u), idesc, 1u);
         }
     }
 }
@@ -261,6 +261,25 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
 // 16 bk + {8+2m, 9+2m} (w = 1); as operand words they go to word columns 8 bk + 2m + w (K order pjr_channel).
 template <bool SPLIT>
 __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2], const PairConsts &k) {
+#ifdef PESTO_X_LD4
+    {   // the chunk's four accumulator loads in flight together, one wait
+        uint32_t r[2][2][8];
+#pragma unroll
+        for (int bk = 0; bk < 2; ++bk)
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) tc::tmem_ld_16x256b_x2(tchunk + 16 * bk + ((uint32_t)(16 * hb) << 16), r[bk][hb]);
+        tc::wait_ld();
+#pragma unroll
+        for (int bk = 0; bk < 2; ++bk)
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                y[bk][2 * hb][0] = add2(y[bk][2 * hb][0], pk2u(r[bk][hb][0], r[bk][hb][1]));
+                y[bk][2 * hb + 1][0] = add2(y[bk][2 * hb + 1][0], pk2u(r[bk][hb][2], r[bk][hb][3]));
+                y[bk][2 * hb][1] = add2(y[bk][2 * hb][1], pk2u(r[bk][hb][4], r[bk][hb][5]));
+                y[bk][2 * hb + 1][1] = add2(y[bk][2 * hb + 1][1], pk2u(r[bk][hb][6], r[bk][hb][7]));
+            }
+    }
+#else
 #pragma unroll
     for (int bk = 0; bk < 2; ++bk)
 #pragma unroll
@@ -273,6 +292,7 @@ __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2]
             y[bk][2 * hb][1] = add2(y[bk][2 * hb][1], pk2u(r[4], r[5]));
             y[bk][2 * hb + 1][1] = add2(y[bk][2 * hb + 1][1], pk2u(r[6], r[7]));
         }
+#endif
     uint32_t hi[2][4][2], lo[2][4][2];
 #pragma unroll
     for (int bk = 0; bk < 2; ++bk)
@@ -361,8 +381,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int hwarp_u = __shfl_sync(FULLM, hwarp, 0), H_u = __shfl_sync(FULLM, H, 0);
     const uint32_t tbase = __shfl_sync(FULLM, *tmem_slot, 0) + (uint32_t)H_u * 256u;
     const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t img_hi = tc::smem_u32(smem_raw), img_lo = img_hi + tcimg::IMG;
-    const uint32_t ext_hi_s = img_hi + SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI;
+    const uint32_t img14 = tc::smem_u32(smem_raw) >> 4;                     // operand descriptors: base in 16-byte units
+    const uint32_t ext14 = img14 + ((SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI) >> 4);
     uint64_t *bars_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
     uint32_t ph0 = 0, ph1 = 0;               // parities of this thread's two chunk barriers (2 grp, 2 grp + 1)
@@ -376,9 +396,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int e = ht & 127;                                        // edge slot inside the tile = TMEM lane
     const int a_loc = e / NN, k = e % NN;
-    uint32_t ind[8];                                               // this edge's indicator words (group 1 uses them)
-#pragma unroll
-    for (int u = 0; u < 8; ++u) ind[u] = UMMA ? pat[a_loc * 8 + u] : 0u;
     const int tile0 = (int)blockIdx.x * 2 + H, tstride = (int)gridDim.x * 2;
     // optional phase timeline (debug): CTA 0, first thread of each group of each half, PROF_STAMPS clock stamps per tile
     const bool profiling = prof != nullptr && blockIdx.x == 0 && (ht & 127) == 0;
@@ -387,13 +404,14 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     do {                                                                                                         \
         if (profiling && prof_seq < prof_tiles) prof[((size_t)prof_seq * 4 + H * 2 + grp) * PROF_STAMPS + (kk)] = clock64(); \
     } while (0)
-    // S0 of one tile: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y), U planes -> B1's spare K rows.  It runs one tile AHEAD
-    // (after E3 of the previous tile, when Y is free again), so that the first-layer MMA of a tile executes while
-    // the reduction phase R of the previous tile occupies the CUDA cores.
-    auto stage0 = [&](int tile, int j, const float4 &g) {
-        const float *sI = state_in + (size_t)(min(tile * TA + a_loc, n_atoms - 1) + 1) * SR;
-        float u0v[UMMA ? TA : 1];
-        if (UMMA && grp == 1) {      // U_i of the tile's atoms (consumed at the end of S0; group 1 has the lighter S0)
+    // S0 of one tile in two parts.  s0_compute: gather + A1 = [p_j.r | p_i.r] as packed bf16 words in registers (s0h / s0l)
+    // and the U_i values; s0_store: words -> TMEM (Y), [d, 1(a), d] columns, U planes -> B1's spare K rows.  S0 runs one
+    // tile AHEAD (after E3 of the previous tile, when Y is free again), so that the first-layer MMA of a tile executes
+    // while the reduction phase R of the previous tile occupies the CUDA cores.
+    uint32_t s0h[16], s0l[16];
+    float u0v[UMMA ? TA : 1];
+    auto s0_compute = [&](int tile, int j, const float4 &g) {
+        if (UMMA && grp == 1) {      // U_i of the tile's atoms (group 1 has the lighter S0)
 #pragma unroll
             for (int m = 0; m < TA; ++m) {
                 const int v = e + 128 * m;
@@ -401,54 +419,37 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + col_channel(v & 127));    // column n holds channel col_channel(n)
             }
         }
-        // ---------------------------------------------------------------- S0: A1 = [p_j.r | p_i.r | d, 1(a), d] -> TMEM (Y)
-        // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
-        // group 0: p_j.r, group 1: p_i.r, d
-        const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
         if (grp == 0) {
             // p_j . r through the 16x256b store shape: four neighbouring lanes share an edge row and read one 128-byte
             // line of p_j per component (8 lines per load instruction instead of 32); each thread covers the rows
             // 8k + lane/4 (k < 4) of its warp's 32 edges and the channels 8m .. 8m+7, m = lane % 4
-            uint32_t hiw[4][4], low[4][4];
+            float x[4][8], y[4][8], z[4][8];
+            u64 kx[4], ky[4], kz[4];
+            auto gather_rows = [&](int k4) {          // rows 8 k4 + lane / 4 of this warp's 32 edges
+                const int sl = 8 * k4 + (lane >> 2);
+                const int jk = __shfl_sync(FULLM, j, sl);
+                const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
+                kx[k4] = pk2(rx, rx); ky[k4] = pk2(ry, ry); kz[k4] = pk2(rz, rz);
+                const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
+                tc::ldg256(sJk, x[k4]);
+                tc::ldg256(sJk + 32, y[k4]);
+                tc::ldg256(sJk + 64, z[k4]);
+            };
+            auto dot_rows = [&](int k4) {
 #pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
-                float x[2][8], y[2][8], z[2][8];
-                u64 kx[2], ky[2], kz[2];
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                    const int sl = 8 * (2 * kb + k2) + (lane >> 2);
-                    const int jk = __shfl_sync(FULLM, j, sl);
-                    const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
-                    kx[k2] = pk2(rx, rx); ky[k2] = pk2(ry, ry); kz[k2] = pk2(rz, rz);
-                    const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
-                    tc::ldg256(sJk, x[k2]);
-                    tc::ldg256(sJk + 32, y[k2]);
-                    tc::ldg256(sJk + 64, z[k2]);
+                for (int u = 0; u < 4; ++u) {
+                    const u64 pr = fma2(kz[k4], pk2(z[k4][2 * u], z[k4][2 * u + 1]),
+                                        fma2(ky[k4], pk2(y[k4][2 * u], y[k4][2 * u + 1]), mul2(kx[k4], pk2(x[k4][2 * u], x[k4][2 * u + 1]))));
+                    split2<SPLIT>(pr, kc, s0h[4 * k4 + u], s0l[4 * k4 + u]);     // [row k4][word u]
                 }
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const u64 pr = fma2(kz[k2], pk2(z[k2][2 * u], z[k2][2 * u + 1]),
-                                            fma2(ky[k2], pk2(y[k2][2 * u], y[k2][2 * u + 1]), mul2(kx[k2], pk2(x[k2][2 * u], x[k2][2 * u + 1]))));
-                        split2<SPLIT>(pr, kc, hiw[2 * kb + k2][u], low[2 * kb + k2][u]);
-                    }
-            }
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                const uint32_t ta = tlane + ((uint32_t)(16 * hb) << 16) + TY;
-                const uint32_t h8[8] = {hiw[2 * hb][0], hiw[2 * hb][1], hiw[2 * hb + 1][0], hiw[2 * hb + 1][1],
-                                        hiw[2 * hb][2], hiw[2 * hb][3], hiw[2 * hb + 1][2], hiw[2 * hb + 1][3]};
-                tc::tmem_st_16x256b_x2(ta, h8);
-                if (SPLIT) {
-                    const uint32_t l8[8] = {low[2 * hb][0], low[2 * hb][1], low[2 * hb + 1][0], low[2 * hb + 1][1],
-                                            low[2 * hb][2], low[2 * hb][3], low[2 * hb + 1][2], low[2 * hb + 1][3]};
-                    tc::tmem_st_16x256b_x2(ta + 40, l8);
-                }
-            }
+            };
+            gather_rows(0); gather_rows(1);
+            dot_rows(0); dot_rows(1);
+            gather_rows(2); gather_rows(3);
+            dot_rows(2); dot_rows(3);
         } else {
-            const float *src = sI;
-            uint32_t hi[16], lo[16];
+            const float *src = state_in + (size_t)(min(tile * TA + a_loc, n_atoms - 1) + 1) * SR;
+            const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
 #pragma unroll
             for (int s = 0; s < S; s += 8) {
                 float x[8], y[8], z[8];
@@ -458,15 +459,33 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
                 for (int u = 0; u < 8; u += 2) {
                     const u64 pr = fma2(gz, pk2(z[u], z[u + 1]), fma2(gy, pk2(y[u], y[u + 1]), mul2(gx, pk2(x[u], x[u + 1]))));
-                    split2<SPLIT>(pr, kc, hi[(s + u) >> 1], lo[(s + u) >> 1]);
+                    split2<SPLIT>(pr, kc, s0h[(s + u) >> 1], s0l[(s + u) >> 1]);
                 }
             }
-            tc::tmem_st16(tlane + TY + 16, hi);
-            if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16, lo);
+        }
+    };
+    auto s0_store = [&](const float4 &g) {
+        // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
+        if (grp == 0) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                const uint32_t ta = tlane + ((uint32_t)(16 * hb) << 16) + TY;
+                const uint32_t h8[8] = {s0h[8 * hb + 0], s0h[8 * hb + 1], s0h[8 * hb + 4], s0h[8 * hb + 5],
+                                        s0h[8 * hb + 2], s0h[8 * hb + 3], s0h[8 * hb + 6], s0h[8 * hb + 7]};
+                tc::tmem_st_16x256b_x2(ta, h8);
+                if (SPLIT) {
+                    const uint32_t l8[8] = {s0l[8 * hb + 0], s0l[8 * hb + 1], s0l[8 * hb + 4], s0l[8 * hb + 5],
+                                            s0l[8 * hb + 2], s0l[8 * hb + 3], s0l[8 * hb + 6], s0l[8 * hb + 7]};
+                    tc::tmem_st_16x256b_x2(ta + 40, l8);
+                }
+            }
+        } else {
+            tc::tmem_st16(tlane + TY + 16, s0h);
+            if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16, s0l);
             {
                 uint32_t hd[8], ld[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { hd[u] = ind[u]; ld[u] = 0u; }
+                for (int u = 0; u < 8; ++u) { hd[u] = UMMA ? pat[a_loc * 8 + u] : 0u; ld[u] = 0u; }     // indicator words of this edge's atom
                 uint32_t dh, dl = 0u;
                 split2<SPLIT>(pk2(g.w, 0.f), kc, dh, dl);
                 hd[0] |= dh;                 // k = 64 (x W_d hi) and k = 77 (x W_d lo)
@@ -505,20 +524,33 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             constexpr uint32_t lbo = 128u * 16u;
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                const uint32_t bh = s < 4 ? img_hi + tcimg::B1 + (uint32_t)s * 2u * lbo : ext_hi_s;
-                const uint64_t dh = tc::smem_desc(bh, lbo, 128u);
+                const uint64_t dh = s < 4 ? tc::smem_desc14(img14, tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u)
+                                          : tc::smem_desc14(ext14, 0u, lbo, 128u);
                 tc::umma_ts(tbase + TX, tbase + TY + 8u * s, dh, idesc, s > 0);
                 if (SPLIT) {
                     tc::umma_ts(tbase + TX, tbase + TY + 40u + 8u * s, dh, idesc, 1u);
                     if (s < 4)
                         tc::umma_ts(tbase + TX, tbase + TY + 8u * s,
-                                    tc::smem_desc(img_lo + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
+                                    tc::smem_desc14(img14, tcimg::IMG + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
                 }
             }
             // (full-width MMAs: N = 32 column chunks with separate commits measured slower at nn = 64)
 #pragma unroll
             for (int c = 0; c < 4; ++c) tc::umma_commit(bars_u + c);
         }
+    };
+    // E-stage register mapping (16x256b): this thread owns the rows 8 k + rl (k < 4) of its warp's 32 edges and, in a
+    // 32-column chunk c, the channels 32 c + 8 m4 .. + 7.  T_j of those rows and channels: one 32-byte load per row
+    // and chunk, four lanes reading one 128-byte line.
+    const int m4 = lane & 3, rl = lane >> 2;
+    float tv[2][4][8];
+    auto load_T = [&](int jv, int cc) {
+        int jrow[4];
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr) jrow[kr] = __shfl_sync(FULLM, jv, 8 * kr + rl);
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr)
+            tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 64 * grp + 32 * cc + 8 * m4, tv[cc][kr]);
     };
     int j_next = 0;
     float4 g_next = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -530,7 +562,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (H == 0)
 #endif
         {
-            stage0(tile0, j_next, g_next);
+            s0_compute(tile0, j_next, g_next);
+            s0_store(g_next);
             bar_named(bar_id, HALF_THREADS);
             issue_m1();
         }
@@ -555,19 +588,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(1);
         PROF_STAMP(2);
         PROF_STAMP(3);
-        // E-stage register mapping (16x256b): this thread owns the rows 8 k + rl (k < 4) of its warp's 32 edges and, in a
-        // 32-column chunk c, the channels 32 c + 8 m4 .. + 7.  T_j of those rows and channels: one 32-byte load per row
-        // and chunk, four lanes reading one 128-byte line; first chunk prefetched while the tensor core works
-        const int m4 = lane & 3, rl = lane >> 2;
-        int jrow[4];
-#pragma unroll
-        for (int kr = 0; kr < 4; ++kr) jrow[kr] = __shfl_sync(FULLM, j, 8 * kr + rl);
-        float tv[2][4][8];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-            for (int kr = 0; kr < 4; ++kr)
-                tc::ldg256(nodeT + (size_t)jrow[kr] * NODE_T_STRIDE + 64 * grp + 32 * cc + 8 * m4, tv[cc][kr]);
+        load_T(j, 0);
+        load_T(j, 1);
         PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
@@ -604,16 +626,21 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(5);
         bar_named(bar_id, HALF_THREADS);
         PROF_STAMP(6);
-        if (hwarp_u == 0 && tc::elect_one()) {                           // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2)
+        // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2).  Each column group issues the GEMMs it consumes itself (an issuing
+        // warp is held back while the tensor-core queue drains, so it should only wait for its own results); separate
+        // commits: the ELU stage of the first chunks overlaps the remaining MMAs
+        if (hwarp_u == 0 && tc::elect_one()) {
             tc::fence_after_sync();
-            // separate commits: the ELU stage of the first chunks overlaps the remaining MMAs
-            issue_gemm<SPLIT, 4, 64, 64>(tbase, TY + 64, TX + 64, 16, img_hi + tcimg::B2V, img_lo + tcimg::B2V);
+            issue_gemm<SPLIT, 2, 32, 32, tcimg::B2Q>(tbase, TY + 0, TX + 0, 16, img14);
+            tc::umma_commit(bars_u + 0);
+            issue_gemm<SPLIT, 2, 32, 32, tcimg::B2P>(tbase, TY + 32, TX + 32, 16, img14);
+            tc::umma_commit(bars_u + 1);
+        }
+        if (hwarp_u == 4 && tc::elect_one()) {
+            tc::fence_after_sync();
+            issue_gemm<SPLIT, 4, 64, 64, tcimg::B2V>(tbase, TY + 64, TX + 64, 16, img14);
             tc::umma_commit(bars_u + 2);
             tc::umma_commit(bars_u + 3);
-            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 0, TX + 0, 16, img_hi + tcimg::B2Q, img_lo + tcimg::B2Q);
-            tc::umma_commit(bars_u + 0);
-            issue_gemm<SPLIT, 2, 32, 32>(tbase, TY + 32, TX + 32, 16, img_hi + tcimg::B2P, img_lo + tcimg::B2P);
-            tc::umma_commit(bars_u + 1);
         }
         ph0 ^= 1u;
         ph1 ^= 1u;
@@ -639,14 +666,18 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(8);
         bar_named(bar_id, HALF_THREADS);
         PROF_STAMP(9);
-        if (hwarp_u == 0 && tc::elect_one()) {                           // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]
+        // M3: D3 (X) = [eqkm.4 | epkm.4 | evm.4]; Kq | Kp for group 0 (attention weights), V0 | V1 for group 1
+        if (hwarp_u == 0 && tc::elect_one()) {
             tc::fence_after_sync();
-            issue_gemm<SPLIT, 2, 16, 16>(tbase, TX + 0, TY + 0, 16, img_hi + tcimg::B3Q, img_lo + tcimg::B3Q);
-            issue_gemm<SPLIT, 2, 16, 16>(tbase, TX + 16, TY + 32, 16, img_hi + tcimg::B3P, img_lo + tcimg::B3P);
-            tc::umma_commit(bars_u + 0);                                 // Kq | Kp: group 0 (attention weights)
+            issue_gemm<SPLIT, 2, 16, 16, tcimg::B3Q>(tbase, TX + 0, TY + 0, 16, img14);
+            issue_gemm<SPLIT, 2, 16, 16, tcimg::B3P>(tbase, TX + 16, TY + 32, 16, img14);
+            tc::umma_commit(bars_u + 0);
             tc::umma_commit(bars_u + 1);                                 // (keeps three phases per tile on every barrier)
-            issue_gemm<SPLIT, 4, 64, 64>(tbase, TX + 32, TY + 64, 16, img_hi + tcimg::B3V, img_lo + tcimg::B3V);
-            tc::umma_commit(bars_u + 2);                                 // V0 | V1: group 1
+        }
+        if (hwarp_u == 4 && tc::elect_one()) {
+            tc::fence_after_sync();
+            issue_gemm<SPLIT, 4, 64, 64, tcimg::B3V>(tbase, TX + 32, TY + 64, 16, img14);
+            tc::umma_commit(bars_u + 2);
             tc::umma_commit(bars_u + 3);
         }
         ph0 ^= 1u;
@@ -679,14 +710,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (grp == 0) {
             // attention weights of this edge (src/model_operations.py:139-140) -> Ws row, every weight duplicated
             // into a pair so that the reduction below can use packed FMAs without register shuffling
-            uint32_t r[32];
-            tc::tmem_ld32(tlane + TX, r);                               // [0,3) Kq, [16,25) Kp
+            uint32_t rq[4], rp[16];
+            tc::tmem_ld4(tlane + TX, rq);                               // [0,3) Kq
+            tc::tmem_ld16(tlane + TX + 16, rp);                         // [16,25) Kp
             tc::wait_ld();
             float kq[3], kp[9];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) kq[u] = __uint_as_float(r[u]) + b3[u];
+            for (int u = 0; u < 3; ++u) kq[u] = __uint_as_float(rq[u]) + b3[u];
 #pragma unroll
-            for (int u = 0; u < 9; ++u) kp[u] = __uint_as_float(r[16 + u]) + b3[16 + u];
+            for (int u = 0; u < 9; ++u) kp[u] = __uint_as_float(rp[u]) + b3[16 + u];
             float lq[NH], lp[NH][3];
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
@@ -744,17 +776,20 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     if (alive) alive = tc::mbar_wait(bar1, ph1, &g_tc_watchdog, 3);
                     tc::fence_after_sync();
                 }
-                uint32_t r[32];
-                tc::tmem_ld32(tlane + TX + 32 + 32 * half, r);
-                tc::wait_ld();
-                float4 *dst = reinterpret_cast<float4 *>(Vs + e * VS_STRIDE + 32 * half);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b3 + 32 + 32 * half + 4 * u);
-                    ulonglong2 o;
-                    o.x = add2(pk2u(r[4 * u], r[4 * u + 1]), bb.x);
-                    o.y = add2(pk2u(r[4 * u + 2], r[4 * u + 3]), bb.y);
-                    *reinterpret_cast<ulonglong2 *>(dst + u) = o;
+                for (int q16 = 0; q16 < 2; ++q16) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tlane + TX + 32 + 32 * half + 16 * q16, r);
+                    tc::wait_ld();
+                    float4 *dst = reinterpret_cast<float4 *>(Vs + e * VS_STRIDE + 32 * half + 16 * q16);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b3 + 32 + 32 * half + 16 * q16 + 4 * u);
+                        ulonglong2 o;
+                        o.x = add2(pk2u(r[4 * u], r[4 * u + 1]), bb.x);
+                        o.y = add2(pk2u(r[4 * u + 2], r[4 * u + 3]), bb.y);
+                        *reinterpret_cast<ulonglong2 *>(dst + u) = o;
+                    }
                 }
             }
         }
@@ -762,9 +797,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         ph1 ^= 1u;
         PROF_STAMP(18);
         if (more) {
-            if (grp == 0 && alive) alive = tc::mbar_wait(bars + 3, ph1 ^ 1u, &g_tc_watchdog, 3);   // every MMA of M3 has read Y
+            // every MMA of M3 has read Y: each group has waited for its own GEMMs, now for the other group's last commit
+            if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, &g_tc_watchdog, 3);
             tc::fence_after_sync();
-            stage0(tile + tstride, jn, gn);
+            s0_compute(tile + tstride, jn, gn);      // (moving this into the shadow of M3 measured slower: profiles/README.md)
+            s0_store(gn);
         }
         // p_j of the reduction group's 8 edges (phase R): issued before the barrier so that part of the gather latency overlaps it
         u64 pjr[8][3];

@@ -39,6 +39,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
@@ -157,6 +171,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// The same descriptor from the operand region's base address in 16-byte units (base14 = smem address >> 4, a uniform
+// value computed once per kernel) plus a compile-time byte offset: one add on the low word, constant high word.
+// (Shared memory is < 256 KB, so base14 + offset never carries into the lbo field.)
+__device__ __forceinline__ uint64_t smem_desc14(uint32_t base14, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = base14 + ((off_bytes >> 4) + (((lbo_bytes >> 4) & 0x3FFFu) << 16));
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 accumulation:
 // c_format=F32 [4,6), a_format=BF16 [7,10), b_format=BF16 [10,13), n>>3 [17,23), m>>4 [24,29)
