@@ -152,6 +152,21 @@ int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int 
  * int64) for the first max_tiles tiles of each half; buf == NULL switches it off. */
 int pesto_debug_edge_timeline(void *buf, int max_tiles);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side PDB text parser (no device work; every pointer is a HOST pointer).  Replaces the gemmi call inside
+ * read_pdb                                                                  src/structure_io.py:6-55
+ * ATOM / HETATM records, fixed columns, lines cut at 80 characters; models from MODEL/ENDMDL; separated parts of a
+ * chain merged per model (gemmi's chain order); altloc duplicates dropped with the reference's key
+ * (chain, residue number, atom name).  Outputs are fixed-width character fields (NUL padded, not terminated):
+ * name4 [cap,4], element2 [cap,2] (title case), resname3 [cap,3], het [cap] ('A' | 'H'), chain [cap], icode [cap]
+ * (0 = none); xyz [cap,3], bfactor [cap] fp32; resid, model int32.  *n_out = atoms found; PESTO_EINVAL if it
+ * exceeds `capacity` (pesto_pdb_count_atoms_host gives an upper bound).
+ * ------------------------------------------------------------------------------------------- */
+int pesto_pdb_count_atoms_host(const char *text, size_t len);
+int pesto_pdb_parse_host(const char *text, size_t len, int capacity, float *xyz, char *name4, char *element2,
+                         char *resname3, int32_t *resid, char *het, char *chain, int32_t *model, char *icode,
+                         float *bfactor, int *n_out);
+
 /* number of kernels one pesto_forward / pesto_knn call launches (for bench.py's gpu_launches) */
 int pesto_forward_launch_count(const pesto_model_t *m, int dense_m, int mode);
 int pesto_knn_launch_count(void);

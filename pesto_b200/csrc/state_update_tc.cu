@@ -259,10 +259,9 @@ __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint3
 // chunk) += accumulator; ELU; bf16 hi | lo words stored in place over the chunk: [0,16) hi words, [16,32) lo words.
 // Thread (rl = lane / 4, m = lane % 4): rows 8 k + rl; block bk, word w <-> columns 16 bk + {2m, 2m+1} (w = 0) and
 // 16 bk + {8+2m, 9+2m} (w = 1); as operand words they go to word columns 8 bk + 2m + w (K order pjr_channel).
-template <bool SPLIT>
+template <bool SPLIT, bool LD4>
 __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2], const PairConsts &k) {
-#ifdef PESTO_X_LD4
-    {   // the chunk's four accumulator loads in flight together, one wait
+    if (LD4) {   // the chunk's four accumulator loads in flight together, one wait (nn >= 16; spills at nn = 8)
         uint32_t r[2][2][8];
 #pragma unroll
         for (int bk = 0; bk < 2; ++bk)
@@ -278,8 +277,7 @@ __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2]
                 y[bk][2 * hb][1] = add2(y[bk][2 * hb][1], pk2u(r[bk][hb][4], r[bk][hb][5]));
                 y[bk][2 * hb + 1][1] = add2(y[bk][2 * hb + 1][1], pk2u(r[bk][hb][6], r[bk][hb][7]));
             }
-    }
-#else
+    } else {
 #pragma unroll
     for (int bk = 0; bk < 2; ++bk)
 #pragma unroll
@@ -292,7 +290,7 @@ __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2]
             y[bk][2 * hb][1] = add2(y[bk][2 * hb][1], pk2u(r[4], r[5]));
             y[bk][2 * hb + 1][1] = add2(y[bk][2 * hb + 1][1], pk2u(r[6], r[7]));
         }
-#endif
+    }
     uint32_t hi[2][4][2], lo[2][4][2];
 #pragma unroll
     for (int bk = 0; bk < 2; ++bk)
@@ -619,7 +617,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
             if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 1);
             tc::fence_after_sync();
-            estage_finish<SPLIT>(tlane + TX + 32 * c, y, kc);
+            estage_finish<SPLIT, (NN >= 16)>(tlane + TX + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();
@@ -659,7 +657,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
             if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 2);
             tc::fence_after_sync();
-            estage_finish<SPLIT>(tlane + TY + 32 * c, y, kc);
+            estage_finish<SPLIT, (NN >= 16)>(tlane + TY + 32 * c, y, kc);
         }
         tc::wait_st();
         tc::fence_before_sync();

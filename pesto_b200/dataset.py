@@ -32,3 +32,30 @@ def collate_batch_features(batch_data, max_num_nn=64, sparse_membership=False):
         a0 += na
         r0 += nr
     return X, ids_topk, q, M
+
+
+class StructuresDataset(torch.utils.data.Dataset):
+    """PDB files -> preprocessed subunits, like src/dataset.py:115-156: `dataset[i]` returns `(subunits, path)` -- or
+    `(structure, path)` without preprocessing, or `(None, path)` (after printing a ReadError line) when the file
+    cannot be parsed.  Parsing uses the gemmi-free C++ reader (pesto_b200.structure_io.read_pdb)."""
+
+    def __init__(self, pdb_filepaths, with_preprocessing=True):
+        super().__init__()
+        self.pdb_filepaths = pdb_filepaths
+        self.with_preprocessing = with_preprocessing
+
+    def __len__(self):
+        return len(self.pdb_filepaths)
+
+    def __getitem__(self, i):
+        from .structure_io import read_pdb
+        from .structure import preprocess_structure
+        pdb_filepath = self.pdb_filepaths[i]
+        try:
+            structure = read_pdb(pdb_filepath)
+        except Exception as e:                                    # noqa: BLE001 -- reference behaviour: report and go on
+            print(f"ReadError: {pdb_filepath}: {e}")
+            return None, pdb_filepath
+        if self.with_preprocessing:
+            return preprocess_structure(structure), pdb_filepath
+        return structure, pdb_filepath
