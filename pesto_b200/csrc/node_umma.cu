@@ -238,25 +238,40 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
 #pragma unroll
         for (int k = 0; k < 4; ++k) rowc[k] = min(rbase + 8 * k, n_rows - 1);
 
-        // operand (K = 64, global order) <- 64 consecutive floats of each row of a global array
-        auto build_a_global = [&](const float *src, int row_stride, int col0, uint32_t a_col) {
+        // operand (K = 64, global order) <- 64 consecutive floats of each row of Z, in two steps so that the loads of the
+        // next operand are in flight while the previous one is converted and multiplied
+        auto load_z = [&](int col0, float (&v)[2][4][8]) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                float v[4][8];
+            for (int b = 0; b < 2; ++b)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tc::ldg256(src + (size_t)rowc[k] * row_stride + col0 + 32 * b + 8 * m, v[k]);
+                for (int k = 0; k < 4; ++k) tc::ldg256(Z + (size_t)rowc[k] * 256 + col0 + 32 * b + 8 * m, v[b][k]);
+        };
+        auto conv_z = [&](const float (&v)[2][4][8], uint32_t a_col) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     uint32_t hi[4][2], lo[4][2];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        nsplit<SPLIT>(v[k][4 * g], v[k][4 * g + 1], hi[k][0], lo[k][0]);
-                        nsplit<SPLIT>(v[k][4 * g + 2], v[k][4 * g + 3], hi[k][1], lo[k][1]);
+                        nsplit<SPLIT>(v[b][k][4 * g], v[b][k][4 * g + 1], hi[k][0], lo[k][0]);
+                        nsplit<SPLIT>(v[b][k][4 * g + 2], v[b][k][4 * g + 3], hi[k][1], lo[k][1]);
                     }
                     store_a8<SPLIT>(tq + a_col + 16 * b + 8 * g, tq + a_col + 32 + 16 * b + 8 * g, hi, lo);
                 }
-            }
         };
+        // previous state of this thread's rows, 16-column half g: [0] = q, [1 + c] = p_c; [row k][columns 2m.. | 8 + 2m..]
+        auto load_state = [&](int g, float2 (&so)[4][4][2]) {
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float *sp = state_prev + (size_t)rowc[k] * SR + 32 * sgm + 16 * g + 2 * m;
+                    so[sgm][k][0] = tc::ldg64(sp);
+                    so[sgm][k][1] = tc::ldg64(sp + 8);
+                }
+        };
+        float2 so[2][4][4][2];
         // operand (K = 32, register order) <- ELU(accumulator[32 columns] + bias)
         auto build_a_elu32 = [&](uint32_t d_col, const float *bias, uint32_t a_col) {
 #pragma unroll
@@ -276,37 +291,45 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
         };
 
         if (FUSE_PREV) {
-            // ---- tail: q1 = Zq . qpm.0, dp[c] = Zp[c] . ppm.0 (operands double-buffered in A0 / A1)
-            build_a_global(Z, 256, 0, A0);
+            // ---- tail: q1 = Zq . qpm.0, dp[c] = Zp[c] . ppm.0 (operands double-buffered in A0 / A1, their Z columns
+            //      double-buffered in registers one step ahead)
+            float za[2][4][8], zb[2][4][8];
+            load_z(0, za);
+            load_z(64, zb);
+            conv_z(za, A0);
             sync_tmem();
             if (warp_u == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 node_gemm<SPLIT, 4, 32>(tbase, DC + 0, A0, 32, sb + nimg::T_WQ1, sb + nimg::T_WQ1 + 4096);
                 tc::umma_commit(bars);
             }
-            build_a_global(Z, 256, 64, A1);
+            load_z(128, za);
+            conv_z(zb, A1);
             sync_tmem();
             if (warp_u == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 node_gemm<SPLIT, 4, 32>(tbase, DC + 32, A1, 32, sb + nimg::T_WP, sb + nimg::T_WP + 4096);
                 tc::umma_commit(bars + 1);
             }
+            load_z(192, zb);
             wait_a();
-            build_a_global(Z, 256, 128, A0);
+            conv_z(za, A0);
             sync_tmem();
             if (warp_u == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 node_gemm<SPLIT, 4, 32>(tbase, DC + 64, A0, 32, sb + nimg::T_WP, sb + nimg::T_WP + 4096);
                 tc::umma_commit(bars);
             }
+            load_state(0, so[0]);                                // previous state: in flight under the rest of the tail
             wait_b();
-            build_a_global(Z, 256, 192, A1);
+            conv_z(zb, A1);
             sync_tmem();
             if (warp_u == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 node_gemm<SPLIT, 4, 32>(tbase, DC + 96, A1, 32, sb + nimg::T_WP, sb + nimg::T_WP + 4096);
                 tc::umma_commit(bars + 1);
             }
+            load_state(1, so[1]);
             // ---- qpm layers 2 and 3 (src/model_operations.py:71-77)
             wait_a();                                            // dp[1] done: A0 is free; q1 was done before it
             build_a_elu32(DC + 0, tbias, A0);
@@ -329,6 +352,10 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
         }
 
         // ---- new state record (residuals :151-152) and, for the next layer, x = [q | |p|] as the operand in A0
+        if (!FUSE_PREV) {
+            load_state(0, so[0]);
+            load_state(1, so[1]);
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             float q[4][4], pn2[4][4];
@@ -337,8 +364,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
             if (FUSE_PREV) load_d16(tq + DC + 16 * g, q);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float *sp = state_prev + (size_t)rowc[k] * SR + 16 * g + 2 * m;
-                const float2 o0 = __ldg(reinterpret_cast<const float2 *>(sp)), o1 = __ldg(reinterpret_cast<const float2 *>(sp + 8));
+                const float2 o0 = so[g][0][k][0], o1 = so[g][0][k][1];
                 if (FUSE_PREV && rowc[k] > 0) {                  // row 0 = sink: stays zero
                     q[k][0] += bq0.x + o0.x; q[k][1] += bq0.y + o0.y; q[k][2] += bq1.x + o1.x; q[k][3] += bq1.y + o1.y;
                 } else {
@@ -358,8 +384,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                 if (FUSE_PREV) load_d16(tq + DC + 32 + 32 * c + 16 * g, p);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float *sp = state_prev + (size_t)rowc[k] * SR + 32 + 32 * c + 16 * g + 2 * m;
-                    const float2 o0 = __ldg(reinterpret_cast<const float2 *>(sp)), o1 = __ldg(reinterpret_cast<const float2 *>(sp + 8));
+                    const float2 o0 = so[g][1 + c][k][0], o1 = so[g][1 + c][k][1];
                     if (FUSE_PREV && rowc[k] > 0) {
                         p[k][0] += o0.x; p[k][1] += o0.y; p[k][2] += o1.x; p[k][3] += o1.y;
                     } else {

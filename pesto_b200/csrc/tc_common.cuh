@@ -219,6 +219,13 @@ __device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
                  : "l"(p));
 }
 
+// 64-bit read-only global load with a fixed place in the instruction stream (volatile: the compiler keeps the issue point)
+__device__ __forceinline__ float2 ldg64(const float *p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 // ---- bf16 splitting --------------------------------------------------------------------------------------------
 // pack two floats into bf16x2 (round to nearest even): low half = a, high half = b
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

@@ -116,3 +116,18 @@ def test_lpt_partition_balances_cost():
         assert sorted(i for s in shards for i in s) == list(range(500))
         loads = [sum(int(costs[i]) for i in s) for s in shards]
         assert max(loads) <= 1.02 * (sum(loads) / g) + costs.max()
+
+
+def test_runner_packing_and_encoding():
+    """host side of the structure runner: greedy packing under the atom budget, residue index = rank of the resid among
+    the structure's sorted unique resids (src/data_encoding.py:73) offset per structure, element one-hot [N,30]."""
+    import numpy as np
+    from pesto_b200.runner import encode_batch, pack_batches
+    assert pack_batches([5, 5, 5], 10) == [[0, 1], [2]]
+    assert pack_batches([50], 10) == [[0]] and pack_batches([], 10) == []
+    a = {"xyz": np.zeros((4, 3)), "element": np.array(["C", "N", "Zz", "O"]), "resid": np.array([7, 7, 3, 9])}
+    b = {"xyz": np.ones((2, 3)), "element": np.array(["S", "C"]), "resid": np.array([1, 2])}
+    X, q0, rid, n_at, n_rs = encode_batch([a, b])
+    assert X.shape == (6, 3) and X.dtype == np.float32 and q0.shape == (6, 30)
+    assert list(q0.argmax(1)) == [0, 2, 29, 1, 3, 0]
+    assert list(rid) == [1, 1, 0, 2, 3, 4] and rid.dtype == np.int32 and n_at == [4, 2] and n_rs == [3, 2]
