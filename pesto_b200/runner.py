@@ -29,12 +29,28 @@ def pack_batches(sizes, target=TARGET_ATOMS_PER_BATCH):
     return batches
 
 
-def encode_batch(structures):
-    """Host side of one batch: X [N,3] f32, q0 [N,30] f32 (element one-hot, src/data_encoding.py:78-84), residue index
-    [N] int32 (position of the atom's resid among the structure's sorted unique resids, src/data_encoding.py:73, plus
-    the batch's residue offset), per-structure atom and residue counts."""
+_EL_SORT = np.argsort(std_elements)
+_EL_SORTED = std_elements[_EL_SORT]
+
+
+def element_index(elements):
+    """Column of every atom in the element one-hot of src/data_encoding.py:56-58,78-84: position in std_elements, or
+    len(std_elements) (= "unknown", the last column) -- as uint8, via one binary search instead of a [N, 29] comparison."""
+    el = np.asarray(elements)
+    pos = np.minimum(np.searchsorted(_EL_SORTED, el), len(_EL_SORTED) - 1)
+    return np.where(_EL_SORTED[pos] == el, _EL_SORT[pos], len(std_elements)).astype(np.uint8)
+
+
+def encode_batch(structures, as_index=False):
+    """Host side of one batch: X [N,3] f32, q0 [N,30] f32 (element one-hot, src/data_encoding.py:78-84; with as_index
+    the uint8 column index instead, expanded on the device), residue index [N] int32 (position of the atom's resid among
+    the structure's sorted unique resids, src/data_encoding.py:73, plus the batch's residue offset), per-structure atom
+    and residue counts."""
     X = np.concatenate([np.asarray(s["xyz"], dtype=np.float32) for s in structures], axis=0)
-    q0 = np.concatenate([onehot(s["element"], std_elements) for s in structures], axis=0).astype(np.float32)
+    if as_index:
+        q0 = np.concatenate([element_index(s["element"]) for s in structures], axis=0)
+    else:
+        q0 = np.concatenate([onehot(s["element"], std_elements) for s in structures], axis=0).astype(np.float32)
     rids, n_res, r0 = [], [], 0
     for s in structures:
         u, inv = np.unique(np.asarray(s["resid"]), return_inverse=True)
@@ -44,34 +60,68 @@ def encode_batch(structures):
     return X, q0, np.concatenate(rids).astype(np.int32), [len(s["xyz"]) for s in structures], n_res
 
 
+class _PinnedSlot:
+    """Reusable pinned staging buffers of one pipeline slot (allocating pinned memory per batch costs milliseconds)."""
+
+    def __init__(self):
+        self.buf = {}
+        self.copied = None          # event: the slot's last H2D copies have completed
+
+    def put(self, name, arr):
+        t = self.buf.get(name)
+        if t is None or t.numel() < arr.size or t.dtype != torch.from_numpy(arr[:0]).dtype:
+            t = torch.empty(max(arr.size, 1) * 5 // 4, dtype=torch.from_numpy(arr[:0]).dtype).pin_memory()
+            self.buf[name] = t
+        v = t[:arr.size].view(arr.shape)
+        v.numpy()[...] = arr
+        return v
+
+
 def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATOMS_PER_BATCH, num_nn=64):
     """Yield (index, z[n_res, 5] float32 on the host) for every structure dictionary (keys xyz, element, resid), in order.
-    The next batch's inputs are staged (pinned, non-blocking) on a copy stream while the current batch computes."""
+
+    Pipeline per batch k: (1) its kNN + forward + logits D2H are enqueued, (2) the host encodes batch k+1 and enqueues
+    its pinned H2D copies on a copy stream while the GPU works, (3) the host waits for batch k's logits."""
     dev = torch.device(device)
     sizes = [len(s["xyz"]) for s in structures]
     batches = pack_batches(sizes, target_atoms)
     copy_stream = torch.cuda.Stream(dev)
+    slots = [_PinnedSlot(), _PinnedSlot()]
 
-    def stage(b):
-        X, q0, rid, n_at, n_rs = encode_batch([structures[i] for i in b])
-        host = [torch.from_numpy(a).pin_memory() for a in (X, q0, rid)]
+    def stage(k):
+        slot = slots[k % 2]
+        if slot.copied is not None:
+            slot.copied.synchronize()                       # the buffers' previous copies are long done
+        X, el, rid, n_at, n_rs = encode_batch([structures[i] for i in batches[k]], as_index=True)
+        host = [slot.put(n, a) for n, a in (("X", X), ("el", el), ("rid", rid))]
         with torch.cuda.stream(copy_stream):
             on_dev = [t.to(dev, non_blocking=True) for t in host]
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
-        return on_dev, host, ready, n_at, n_rs
+            # one byte per atom crosses PCIe; the [N, 30] one-hot Model.forward takes is expanded on the device
+            on_dev[1] = torch.nn.functional.one_hot(on_dev[1].long(), len(std_elements) + 1).to(torch.float32)
+            slot.copied = torch.cuda.Event()
+            slot.copied.record(copy_stream)
+        return on_dev, slot.copied, n_at, n_rs
 
-    nxt = stage(batches[0]) if batches else None
+    nxt = stage(0) if batches else None
+    zpin = [None, None]
     with torch.no_grad():
         for k, b in enumerate(batches):
-            (Xd, q0d, ridd), _host, ready, n_at, n_rs = nxt
-            torch.cuda.current_stream(dev).wait_event(ready)
+            (Xd, q0d, ridd), ready, n_at, n_rs = nxt
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(ready)
             for t in (Xd, q0d, ridd):
-                t.record_stream(torch.cuda.current_stream(dev))
-            nxt = stage(batches[k + 1]) if k + 1 < len(batches) else None
+                t.record_stream(main)
             ids1 = batch_topology(Xd, n_at, num_nn)
-            z = model(Xd, ids1, q0d, ridd, n_res=int(sum(n_rs))).cpu()
+            z = model(Xd, ids1, q0d, ridd, n_res=int(sum(n_rs)))
+            if zpin[k % 2] is None or zpin[k % 2].shape[0] < z.shape[0]:
+                zpin[k % 2] = torch.empty((z.shape[0] * 5 // 4, 5), dtype=torch.float32).pin_memory()
+            zh = zpin[k % 2][:z.shape[0]]
+            zh.copy_(z, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            nxt = stage(k + 1) if k + 1 < len(batches) else None      # host work of the next batch under this batch's GPU work
+            done.synchronize()
             r0 = 0
             for i, nr in zip(b, n_rs):
-                yield i, z[r0:r0 + nr]
+                yield i, zh[r0:r0 + nr].clone()
                 r0 += nr

@@ -131,3 +131,8 @@ def test_runner_packing_and_encoding():
     assert X.shape == (6, 3) and X.dtype == np.float32 and q0.shape == (6, 30)
     assert list(q0.argmax(1)) == [0, 2, 29, 1, 3, 0]
     assert list(rid) == [1, 1, 0, 2, 3, 4] and rid.dtype == np.int32 and n_at == [4, 2] and n_rs == [3, 2]
+    from pesto_b200.data_encoding import onehot, std_elements
+    from pesto_b200.runner import element_index
+    els = np.array(list(std_elements) + ["X", "", "Zz", "H", "c"])
+    assert list(element_index(els)) == list(onehot(els, std_elements).argmax(1))
+    assert list(encode_batch([a, b], as_index=True)[1]) == [0, 2, 29, 1, 3, 0]
