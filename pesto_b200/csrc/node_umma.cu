@@ -125,7 +125,13 @@ constexpr uint32_t A0 = 0, A1 = 64, DC = 128;     // operand regions (64 columns
 constexpr int NSM_BAR = nimg::TOTAL;              // 2 mbarriers + TMEM slot
 constexpr int NSM_TOTAL = NSM_BAR + 32;
 
-__device__ __forceinline__ float n_elu(float x) { return x > 0.f ? x : (expf(x) - 1.0f); }
+// ELU without a branch: max(x, 0) + (exp(min(x, 0)) - 1), one MUFU.EX2 (the edge kernel's formulation)
+__device__ __forceinline__ float n_elu(float x) {
+    const float n = fminf(x, 0.f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(n * LOG2E));
+    return (x - n) + (e - 1.0f);
+}
 
 // (a, b) -> bf16x2 hi word and, if SPLIT, the bf16x2 word of the remainders
 template <bool SPLIT>
