@@ -238,6 +238,22 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
     };
 
     const int n_tiles = (n_rows + 127) / 128;
+    // the first two 64-column pieces of a tile's Z rows: loaded one tile ahead (under the wait for the U GEMM of the
+    // previous tile), so that a tile starts with its operands in registers instead of with an exposed HBM round trip
+    float za[2][4][8], zb[2][4][8];
+    auto load_z_tile = [&](int tile_, int col0, float (&v)[2][4][8]) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int row = min(tile_ * 128 + warp * 32 + rl + 8 * k, n_rows - 1);
+                tc::ldg256(Z + (size_t)row * 256 + col0 + 32 * b + 8 * m, v[b][k]);
+            }
+    };
+    if (FUSE_PREV && (int)blockIdx.x < n_tiles) {
+        load_z_tile(blockIdx.x, 0, za);
+        load_z_tile(blockIdx.x, 64, zb);
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int rbase = tile * 128 + warp * 32 + rl;           // row of k = 0; rows rbase + 8 k
         int rowc[4];
@@ -299,10 +315,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
         if (FUSE_PREV) {
             // ---- tail: q1 = Zq . qpm.0, dp[c] = Zp[c] . ppm.0 (operands double-buffered in A0 / A1, their Z columns
             //      double-buffered in registers one step ahead)
-            float za[2][4][8], zb[2][4][8];
-            load_z(0, za);
-            load_z(64, zb);
-            conv_z(za, A0);
+            conv_z(za, A0);                                      // za, zb: loaded one tile ahead
             sync_tmem();
             if (warp_u == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
@@ -467,6 +480,12 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                 node_gemm<SPLIT, 4, 128, 256>(tbase, DC, A0, 32, sb + nimg::H_WTU + 128 * 16, sb + nimg::H_WTU + 32768 + 128 * 16);
                 tc::umma_commit(bars + 1);
             }
+            if (FUSE_PREV) {          // next tile's first operands: in flight under the U GEMM (unconditional, on a clamped
+                                      // tile index: a conditional reload would keep the old values alive across the tile)
+                const int tn = min(tile + (int)gridDim.x, n_tiles - 1);
+                load_z_tile(tn, 0, za);
+                load_z_tile(tn, 64, zb);
+            }
             wait_a();                                            // Q = nqm(x) / sdk: 12 of 16 columns
             {
                 float v[4][4];
@@ -496,6 +515,11 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                         *reinterpret_cast<float2 *>(d + 8) = make_float2(v[k][2] + b1.x, v[k][3] + b1.y);
                     }
             }
+        }
+        if (FUSE_PREV && !NEXT) {
+            const int tn = min(tile + (int)gridDim.x, n_tiles - 1);
+            load_z_tile(tn, 0, za);
+            load_z_tile(tn, 64, zb);
         }
         tc::fence_before_sync();
         __syncthreads();                                         // all TMEM reads of this tile precede the next tile's stores

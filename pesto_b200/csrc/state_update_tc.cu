@@ -326,6 +326,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     constexpr int WPA = NN / SEG;                   // warps (of one group) per atom: 2 for nn = 64
     constexpr int GA = NN / 8;                      // 8-edge reduction groups per atom
     constexpr bool UMMA = NN >= 32;                 // U_i enters through spare K columns of the first MMA
+    constexpr bool TPREF = NN >= 32;                // first T_j chunk loaded one tile ahead (measured slower at nn <= 16)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *img = smem_raw;                                      // weight images + biases (shared by both halves)
     const float *b2 = reinterpret_cast<const float *>(img + tcimg::BIAS);
@@ -562,6 +563,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         {
             s0_compute(tile0, j_next, g_next);
             s0_store(g_next);
+            if (TPREF) {
+                load_T(j_next, 0);
+#ifdef PESTO_X_TPREF2B
+                load_T(j_next, 1);
+#endif
+            }
             bar_named(bar_id, HALF_THREADS);
             issue_m1();
         }
@@ -586,7 +593,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(1);
         PROF_STAMP(2);
         PROF_STAMP(3);
-        load_T(j, 0);
+        // T_j: for nn >= 32 the first chunk (with PESTO_X_TPREF2B: both) was loaded one tile ahead, after the reduction loop
+        if (!TPREF) load_T(j, 0);
+#ifdef PESTO_X_TPREF2B
+        if (!TPREF)
+#endif
         load_T(j, 1);
         PROF_STAMP(4);
 
@@ -699,6 +710,21 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 qv[u] = q4.x; qv[u + 1] = q4.y; qv[u + 2] = q4.z; qv[u + 3] = q4.w;
             }
         }
+        u64 pjr[8][3];       // p_j of this thread's 8-edge reduction group (phase R)
+#define PJR_LOAD()                                                                                                       \
+        {                                                                                                                \
+            const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};          \
+            _Pragma("unroll") for (int ee = 0; ee < 8; ++ee) {                                                           \
+                const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;                                        \
+                _Pragma("unroll") for (int c = 0; c < 3; ++c) pjr[ee][c] = tc::ldg64u(pJ + 32 * c);                      \
+            }                                                                                                            \
+        }
+        // S0 arithmetic of the next tile in the shadow of this tile's third-layer MMA (unconditional for the same reason as
+        // the T_j prefetch: on the last tile it recomputes this tile's words, which are never stored)
+        s0_compute(more ? tile + tstride : tile, jn, gn);
+#ifdef PESTO_X_PJR2
+        PJR_LOAD();
+#endif
         if (alive) alive = tc::mbar_wait(bar0, ph0, &g_tc_watchdog, 3);     // group 0: Kq | Kp; group 1: V0
         tc::fence_after_sync();
         PROF_STAMP(10);
@@ -798,20 +824,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             // every MMA of M3 has read Y: each group has waited for its own GEMMs, now for the other group's last commit
             if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, &g_tc_watchdog, 3);
             tc::fence_after_sync();
-            s0_compute(tile + tstride, jn, gn);      // (moving this into the shadow of M3 measured slower: profiles/README.md)
             s0_store(gn);
         }
         // p_j of the reduction group's 8 edges (phase R): issued before the barrier so that part of the gather latency overlaps it
-        u64 pjr[8][3];
-        {
-            const int jr[8] = {idr[0].x, idr[0].y, idr[0].z, idr[0].w, idr[1].x, idr[1].y, idr[1].z, idr[1].w};
-#pragma unroll
-            for (int ee = 0; ee < 8; ++ee) {
-                const float *pJ = state_in + (size_t)jr[ee] * SR + 32 + 2 * pair;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) pjr[ee][c] = __ldg(reinterpret_cast<const u64 *>(pJ + 32 * c));
-            }
-        }
+#ifndef PESTO_X_PJR2
+        PJR_LOAD();
+#endif
         // ---------------------------------------------------------------- R: attention-weighted sums over the edges
         // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
         {
@@ -867,6 +885,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int c = 0; c < 3; ++c) {
                 P[32 + 32 * c] = zp[c][0];
                 P[48 + 32 * c] = zp[c][1];
+            }
+            if (TPREF) {          // unconditional (row 0 when there is no next tile): a load under `if (more)` would keep tv alive
+                load_T(jn, 0);    // -- and 32 registers occupied -- through the whole tile
+#ifdef PESTO_X_TPREF2B
+                load_T(jn, 1);
+#endif
             }
             bar_named(bar_id, HALF_THREADS);
             PROF_STAMP(14);

@@ -226,6 +226,12 @@ __device__ __forceinline__ float2 ldg64(const float *p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long ldg64u(const void *p) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 // ---- bf16 splitting --------------------------------------------------------------------------------------------
 // pack two floats into bf16x2 (round to nearest even): low half = a, high half = b
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
