@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- atoms/sec of the i_v4_1 forward (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|bf16x3|bf16] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|f16x3|f16] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, no data-path collective)
 
 One "step" = one forward pass (em -> 32 StateUpdate layers -> residue pool -> decoder) over the workload:
@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("PESTO_MODE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("PESTO_MODE", "f16x3"), choices=["fp32", "f16x3", "f16", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -322,7 +322,7 @@ def main():
         out = {
             "metric": METRIC, "value": total_atoms * args.steps / (ms_total * 1e-3), "unit": "atoms/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-term split bf16 on tcgen05, fp32 accumulate/state)", "bf16": "bf16"}[args.mode],
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "f16x3": "f16x3 (3-term split product over fp16 hi/lo planes on tcgen05, fp32 accumulate/state)", "f16": "f16"}[{"bf16x3": "f16x3", "bf16": "f16"}.get(args.mode, args.mode)],
             "data": "fixture: pdbs_test coordinates/elements/residue ids (tests/golden/pdbs_test_53.npz), shipped i_v4_1 checkpoint",
             "config": {"workload": "configs[1]: i_v4_1 (32 layers, k=64, Ns=32) over the 53 pdbs_test structures, one collated batch per step",
                        "atoms_per_step_per_gpu": n_atoms, "residues_per_step_per_gpu": n_res, "structures": len(sizes),

@@ -40,8 +40,11 @@ extern "C" {
 
 /* arithmetic modes of the per-edge MLPs (state, softmax and accumulators are always fp32) */
 #define PESTO_MODE_FP32     0   /* FFMA everywhere: parity mode                                     */
-#define PESTO_MODE_BF16X3   1   /* tcgen05 tensor cores, 3-term split bf16 (hi*hi + lo*hi + hi*lo)  */
-#define PESTO_MODE_BF16     2   /* tcgen05 tensor cores, single bf16 pass: speed mode, ~1e-1 logits */
+#define PESTO_MODE_F16X3    1   /* tcgen05 tensor cores, 3-term split product hi*hi + lo*hi + hi*lo over fp16 planes   */
+                                /* (11 + 11 mantissa bits: fp32-accurate, logits within ~1e-4 of the reference); default */
+#define PESTO_MODE_F16      2   /* tcgen05 tensor cores, single fp16 pass: speed mode, ~2e-2 on the logits              */
+#define PESTO_MODE_BF16X3   PESTO_MODE_F16X3   /* former names (the planes were bf16 until the fp16 planes measured 8x  */
+#define PESTO_MODE_BF16     PESTO_MODE_F16     /* more accurate at the same speed); kept as aliases                      */
 
 typedef struct pesto_model pesto_model_t;
 

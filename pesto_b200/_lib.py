@@ -9,8 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PESTO_B200_LIB: experiment aid (profiles/variants.py builds kernel variants side by side); the default is the in-tree build
 LIB_PATH = os.environ.get("PESTO_B200_LIB") or os.path.join(_HERE, "libpesto_b200.so")
 
-MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+MODE_FP32, MODE_F16X3, MODE_F16 = 0, 1, 2
+MODE_BF16X3, MODE_BF16 = MODE_F16X3, MODE_F16          # former names (see include/pesto_b200.h)
+MODES = {"fp32": MODE_FP32, "f16x3": MODE_F16X3, "f16": MODE_F16, "bf16x3": MODE_F16X3, "bf16": MODE_F16}
 
 _c = ctypes
 _vp, _i, _sz, _i64 = _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_int64

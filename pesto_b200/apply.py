@@ -20,7 +20,7 @@ from .structure import concatenate_chains, encode_bfactor, split_by_chain
 from .structure_io import save_pdb
 
 
-def load_model(model_dir, checkpoint="model_ckpt.pt", mode="bf16x3", device="cuda"):
+def load_model(model_dir, checkpoint="model_ckpt.pt", mode="f16x3", device="cuda"):
     """Model(config_model) + load_state_dict of the shipped checkpoint (apply_model.ipynb cells 2-4)."""
     spec = importlib.util.spec_from_file_location("pesto_reference_config", os.path.join(model_dir, "config.py"))
     cfg = importlib.util.module_from_spec(spec)
@@ -61,7 +61,7 @@ def apply_to_pdb(model, pdb_filepath, device="cuda", out_prefix=None):
 def main():
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--model-dir", required=True, help="directory holding config.py and model_ckpt.pt")
-    ap.add_argument("--mode", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--mode", default="f16x3", choices=["fp32", "f16x3", "f16", "bf16x3", "bf16"])
     ap.add_argument("pdb", nargs="+")
     a = ap.parse_args()
     model = load_model(a.model_dir, mode=a.mode)

@@ -61,18 +61,23 @@ def build_library(force=False, verbose=False):
 
 
 def build_variant(name, defines, src="state_update_tc.cu"):
-    """Experiment aid: the library with `src` recompiled under extra -D defines -> libpesto_b200.<name>.so."""
+    """Experiment aid: the library with `src` (one file name or a list) recompiled under extra -D defines
+    -> libpesto_b200.<name>.so."""
     build_library()
-    obj = os.path.join(CSRC, f"{src[:-3]}.{name}.o")
-    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    with open(obj + ".log", "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed for variant {name}:\n{r.stdout}\n{r.stderr}")
-    objs = [obj if s == src else os.path.join(CSRC, s[:-3] + ".o") for s in SOURCES]
+    srcs = [src] if isinstance(src, str) else list(src)
+    objs = {}
+    for sfile in srcs:
+        obj = os.path.join(CSRC, f"{sfile[:-3]}.{name}.o")
+        cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, sfile), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(obj + ".log", "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for variant {name}:\n{r.stdout}\n{r.stderr}")
+        objs[sfile] = obj
+    link = [objs.get(s, os.path.join(CSRC, s[:-3] + ".o")) for s in SOURCES]
     lib = os.path.join(HERE, f"libpesto_b200.{name}.so")
-    r = subprocess.run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"],
+    r = subprocess.run([NVCC, "-shared", "-o", lib] + link + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

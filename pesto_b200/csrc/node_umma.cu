@@ -45,19 +45,8 @@ size_t node_tc_layer_bytes() { return nimg::TOTAL; }
 
 namespace {
 
-inline uint16_t h_bf16(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-inline float h_f32(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
+inline uint16_t h_bf16(float f) { return tc::h16_from_f32_host(f); }      // (configured 16-bit plane format)
+inline float h_f32(uint16_t h) { return tc::h16_to_f32_host(h); }
 // K position (0..31) of an operand block -> channel, for operand words built from a row piece loaded from global
 // memory (lane m reads channels 8m .. 8m+7 and owns word columns 2m, 2m+1, 8+2m, 9+2m)
 inline int node_k_global(int p) { return p < 16 ? 8 * (p / 4) + p % 4 : 8 * ((p - 16) / 4) + 4 + (p - 16) % 4; }
@@ -136,8 +125,8 @@ __device__ __forceinline__ float n_elu(float x) {
 // (a, b) -> bf16x2 hi word and, if SPLIT, the bf16x2 word of the remainders
 template <bool SPLIT>
 __device__ __forceinline__ void nsplit(float a, float b, uint32_t &hi, uint32_t &lo) {
-    if (SPLIT) tc::split_bf16x2(a, b, hi, lo);
-    else { hi = tc::pack_bf16x2(a, b); lo = 0u; }
+    if (SPLIT) tc::split_h16x2(a, b, hi, lo);
+    else { hi = tc::pack_h16x2(a, b); lo = 0u; }
 }
 
 // fp32 accumulator block (16 columns at taddr, the warp's 32 lanes): v[k][0..3] = row 8k + rl, columns 2m, 2m+1, 8+2m, 9+2m
@@ -168,7 +157,7 @@ __device__ __forceinline__ void store_a8(uint32_t t_hi, uint32_t t_lo, const uin
 // (N = columns of this MMA, NIMG = rows of the [K/8][NIMG][8] weight image the N rows at b_hi / b_lo belong to)
 template <bool SPLIT, int KSTEPS, int N, int NIMG = N>
 __device__ __forceinline__ void node_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t b_hi, uint32_t b_lo) {
-    constexpr uint32_t idesc = tc::idesc_bf16(128, N);
+    constexpr uint32_t idesc = tc::idesc_h16(128, N);
     constexpr uint32_t lbo = (uint32_t)NIMG * 16u;
 #pragma unroll
     for (int s = 0; s < KSTEPS; ++s) {

@@ -53,20 +53,6 @@ static_assert(IMG % 16 == 0 && TOTAL % 16 == 0, "images are copied with 16-byte 
 size_t tc_edge_bytes() { return tcimg::TOTAL; }
 size_t tc_layer_bytes() { return tcimg::TOTAL + node_tc_layer_bytes(); }
 
-static inline uint16_t f32_to_bf16_rne(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-static inline float bf16_to_f32(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
-
 // K position (0..31) of the p_j.r block of A1 -> state channel: the thread with m = lane % 4 gathers channels 8m..8m+7
 // of its row and owns TMEM columns 2m, 2m+1 (first four channels) and 8+2m, 8+2m+1 (last four) of the 16-column plane
 static inline int pjr_channel(int p) { return p < 16 ? 8 * (p / 4) + p % 4 : 8 * ((p - 16) / 4) + 4 + (p - 16) % 4; }
@@ -89,8 +75,8 @@ void pack_tc_layer(const float *blob, void *dst_v) {
     pack_node_tc_layer(blob, dst + tcimg::TOTAL);
     auto put = [&](int img_off, int N, int n, int k, float w) {
         const size_t e = (size_t)(k / 8) * N * 8 + (size_t)n * 8 + (k % 8);
-        const uint16_t hi = f32_to_bf16_rne(w);
-        const uint16_t lo = f32_to_bf16_rne(w - bf16_to_f32(hi));
+        const uint16_t hi = tc::h16_from_f32_host(w);
+        const uint16_t lo = tc::h16_from_f32_host(w - tc::h16_to_f32_host(hi));
         ((uint16_t *)(dst + img_off))[e] = hi;
         ((uint16_t *)(dst + tcimg::IMG + img_off))[e] = lo;
     };
@@ -210,12 +196,14 @@ template <bool SPLIT>
 __device__ __forceinline__ void split2(u64 x, const PairConsts &k, uint32_t &hi, uint32_t &lo) {
     float x0, x1;
     up2(x, x0, x1);
-    hi = tc::pack_bf16x2(x0, x1);
+    hi = tc::pack_h16x2(x0, x1);
     if (SPLIT) {
-        const u64 l = fma2(pk2u(hi << 16, hi & 0xffff0000u), k.neg1, x);
+        float h0, h1;
+        tc::unpack_h16x2(hi, h0, h1);
+        const u64 l = fma2(pk2(h0, h1), k.neg1, x);
         float l0, l1;
         up2(l, l0, l1);
-        lo = tc::pack_bf16x2(l0, l1);
+        lo = tc::pack_h16x2(l0, l1);
     }
 }
 
@@ -239,7 +227,7 @@ __device__ __forceinline__ float seg_sum_tc(float v) {
 // starts B_OFF bytes after the shared-memory base (base14 = base address >> 4), its lo plane tcimg::IMG bytes later
 template <bool SPLIT, int KSTEPS, int N, int NIMG, uint32_t B_OFF>
 __device__ __forceinline__ void issue_gemm(uint32_t tbase, uint32_t d_col, uint32_t a_col, uint32_t lo_off, uint32_t base14) {
-    constexpr uint32_t idesc = tc::idesc_bf16(128, N);
+    constexpr uint32_t idesc = tc::idesc_h16(128, N);
     constexpr uint32_t lbo = (uint32_t)NIMG * 16u;
 #pragma unroll
     for (int s = 0; s < KSTEPS; ++s) {
@@ -366,8 +354,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         uint32_t w = 0;
         if (UMMA && a < TA) {
             const int k0 = 64 + 2 * u, k1 = k0 + 1;
-            if (k0 >= 65 + 3 * a && k0 < 68 + 3 * a) w |= 0x3F80u;
-            if (k1 >= 65 + 3 * a && k1 < 68 + 3 * a) w |= 0x3F800000u;
+            if (k0 >= 65 + 3 * a && k0 < 68 + 3 * a) w |= tc::H16_ONE;
+            if (k1 >= 65 + 3 * a && k1 < 68 + 3 * a) w |= tc::H16_ONE << 16;
         }
         reinterpret_cast<uint32_t *>(smem_raw + SM_PAT)[tid] = w;
     }
@@ -500,15 +488,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int m = 0; m < TA; ++m) {
                 const int v = e + 128 * m, a = v >> 7, n = v & 127;
                 const float u0 = u0v[m];
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(u0);
-                const float r1 = u0 - __bfloat162float(h0);
-                const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-                const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
-                const __nv_bfloat16 hp[3] = {h0, h1, h2};
+                const uint16_t h0 = tc::h16_from_f32(u0);
+                const float r1 = u0 - tc::h16_to_f32(h0);
+                const uint16_t h1 = tc::h16_from_f32(r1);
+                const uint16_t h2 = tc::h16_from_f32(r1 - tc::h16_to_f32(h1));
+                const uint16_t hp[3] = {h0, h1, h2};
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const int kk = 1 + 3 * a + p;        // row 64 + kk; rows 64..71 in K group 0, 72..79 in K group 1
-                    *reinterpret_cast<__nv_bfloat16 *>(ext_hi + (kk >> 3) * 2048 + n * 16 + (kk & 7) * 2) = hp[p];
+                    *reinterpret_cast<uint16_t *>(ext_hi + (kk >> 3) * 2048 + n * 16 + (kk & 7) * 2) = hp[p];
                 }
             }
         }
@@ -519,7 +507,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     auto issue_m1 = [&]() {
         if (hwarp_u == 0 && tc::elect_one()) {                           // M1: D1 (X) = A1 . B1^T, K = 80
             tc::fence_after_sync();
-            constexpr uint32_t idesc = tc::idesc_bf16(128, 128);
+            constexpr uint32_t idesc = tc::idesc_h16(128, 128);
             constexpr uint32_t lbo = 128u * 16u;
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
@@ -1017,8 +1005,8 @@ umma_probe_kernel(const float *__restrict__ A, const float *__restrict__ B, floa
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar;
-    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
-    __nv_bfloat16 *Blo = Bhi + (size_t)N * K;
+    uint16_t *Bhi = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *Blo = Bhi + (size_t)N * K;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
     if (tid == 0) {
@@ -1028,10 +1016,10 @@ umma_probe_kernel(const float *__restrict__ A, const float *__restrict__ B, floa
     for (int e = tid; e < N * K; e += 128) {                  // B image [K/8][N][8]
         int n = e / K, k = e % K;
         float w = B[e];
-        __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const uint16_t h = tc::h16_from_f32(w);
         size_t off = (size_t)(k / 8) * N * 8 + (size_t)n * 8 + (k % 8);
         Bhi[off] = h;
-        Blo[off] = __float2bfloat16_rn(w - __bfloat162float(h));
+        Blo[off] = tc::h16_from_f32(w - tc::h16_to_f32(h));
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -1044,7 +1032,7 @@ umma_probe_kernel(const float *__restrict__ A, const float *__restrict__ B, floa
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
             float a = A[(size_t)tid * K + c0 + 2 * u], b = A[(size_t)tid * K + c0 + 2 * u + 1];
-            tc::split_bf16x2(a, b, hi[u], lo[u]);
+            tc::split_h16x2(a, b, hi[u], lo[u]);
         }
         tc::tmem_st16(lane_addr + c0 / 2, hi);
         tc::tmem_st16(lane_addr + 64 + c0 / 2, lo);
@@ -1094,7 +1082,7 @@ extern "C" int pesto_debug_umma_probe(const float *A, const float *B, float *D, 
         return PESTO_EINVAL;
     }
     uint32_t l = lbo >= 0 ? (uint32_t)lbo : (uint32_t)N * 16, s = sbo >= 0 ? (uint32_t)sbo : 128u;
-    uint32_t id = idesc ? (uint32_t)idesc : tc::idesc_bf16(128, N);
+    uint32_t id = idesc ? (uint32_t)idesc : tc::idesc_h16(128, N);
     size_t smem = (size_t)N * K * 2 * 2;
     PESTO_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, split, l, s, id);

@@ -2,6 +2,7 @@
 // mbarrier, UMMA shared-memory and instruction descriptors, bf16 hi/lo splitting.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -180,10 +181,40 @@ __device__ __forceinline__ uint64_t smem_desc14(uint32_t base14, uint32_t off_by
     const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
     return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 accumulation:
-// c_format=F32 [4,6), a_format=BF16 [7,10), b_format=BF16 [10,13), n>>3 [17,23), m>>4 [24,29)
-__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// 16-bit format of the split operand planes (hi | lo).  Default fp16: 11 + 11 mantissa bits, so the dropped lo x lo term of
+// the 3-term product is ~2^-24 and the product is fp32-accurate (~2^-21); fp16's range (65504, conversions saturate) is
+// ample for this model's activations (|state| <= ~50) and weights.  -DPESTO_SPLIT_BF16 selects bf16
+// planes (8 + 8 bits, error ~2^-16 per product, unlimited range).
+#ifdef PESTO_SPLIT_BF16
+constexpr bool H16_IS_FP16 = false;
+#else
+constexpr bool H16_IS_FP16 = true;
+#endif
+constexpr uint32_t H16_ONE = H16_IS_FP16 ? 0x3C00u : 0x3F80u;       // 1.0
+// Instruction descriptor for kind::f16 (A/B both K-major, both in the configured 16-bit format) and fp32 accumulation:
+// c_format=F32 [4,6), a_format [7,10), b_format [10,13) (0 = F16, 1 = BF16), n>>3 [17,23), m>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_h16(int m, int n) {
+    return (1u << 4) | ((H16_IS_FP16 ? 0u : 1u) << 7) | ((H16_IS_FP16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+// host-side conversions for the weight images
+__host__ inline uint16_t h16_from_f32_host(float f) {
+    if (H16_IS_FP16) {
+        const __half_raw r = __float2half_rn(f);
+        return r.x;
+    }
+    const __nv_bfloat16_raw r = __float2bfloat16_rn(f);
+    return r.x;
+}
+__host__ inline float h16_to_f32_host(uint16_t h) {
+    if (H16_IS_FP16) {
+        __half_raw r;
+        r.x = h;
+        return __half2float(__half(r));
+    }
+    __nv_bfloat16_raw r;
+    r.x = h;
+    return __bfloat162float(__nv_bfloat16(r));
 }
 // D[tmem] (+)= A[tmem] * B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -232,18 +263,36 @@ __device__ __forceinline__ unsigned long long ldg64u(const void *p) {
     return v;
 }
 
-// ---- bf16 splitting --------------------------------------------------------------------------------------------
-// pack two floats into bf16x2 (round to nearest even): low half = a, high half = b
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+// ---- 16-bit splitting ------------------------------------------------------------------------------------------
+// pack two floats into the configured 16-bit format (round to nearest even, saturating): low half = a, high half = b
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
     uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    if (H16_IS_FP16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
-// hi = bf16x2(a, b); lo = bf16x2(a - float(hi.a), b - float(hi.b))
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    hi = pack_bf16x2(a, b);
-    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-    lo = pack_bf16x2(a - ha, b - hb);
+// the two floats of a packed word
+__device__ __forceinline__ void unpack_h16x2(uint32_t w, float &a, float &b) {
+    if (H16_IS_FP16) {
+        asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(a), "=f"(b) : "r"(w));
+    } else {
+        a = __uint_as_float(w << 16);
+        b = __uint_as_float(w & 0xffff0000u);
+    }
+}
+// one float -> 16-bit pattern and back (U planes)
+__device__ __forceinline__ uint16_t h16_from_f32(float f) { return (uint16_t)(pack_h16x2(f, 0.f) & 0xffffu); }
+__device__ __forceinline__ float h16_to_f32(uint16_t h) {
+    float a, b;
+    unpack_h16x2((uint32_t)h, a, b);
+    return a;
+}
+// hi = h16x2(a, b); lo = h16x2(a - float(hi.a), b - float(hi.b))
+__device__ __forceinline__ void split_h16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = pack_h16x2(a, b);
+    float ha, hb;
+    unpack_h16x2(hi, ha, hb);
+    lo = pack_h16x2(a - ha, b - hb);
 }
 
 }  // namespace tc

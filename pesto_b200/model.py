@@ -66,11 +66,12 @@ class Model(torch.nn.Module):
       q0        [N, N0] float32 features
       M         [N, R] float membership (rows one-hot), as the reference; or, as an extension that avoids the dense
                 matrix, a 1-D integer tensor with the residue column of every atom (pass n_res= to skip a sync).
-    `mode`: 'bf16x3' (default: tensor cores, 3-term split bf16, logits within 1e-3 of the reference), 'fp32' (FFMA,
-    exact mode) or 'bf16' (tensor cores, single pass, speed mode with ~1e-1 logit error).
+    `mode`: 'f16x3' (default: tcgen05 tensor cores, 3-term split product over fp16 hi/lo planes, logits within ~1e-4 of
+    the reference), 'fp32' (FFMA, exact mode) or 'f16' (tensor cores, single fp16 pass, speed mode with ~2e-2 logit error).
+    'bf16x3' / 'bf16' are accepted as former names of the two tensor-core modes.
     """
 
-    def __init__(self, config, mode="bf16x3"):
+    def __init__(self, config, mode="f16x3"):
         super().__init__()
         for lp in config["sum"]:
             if (lp["Ns"], lp["Nh"], lp["Nk"]) != (32, 2, 3) or lp["nn"] not in (8, 16, 32, 64):

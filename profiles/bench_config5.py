@@ -21,7 +21,7 @@ from pesto_b200.synth import synth_structure, interfaceome_sizes, BASE_SEED   # 
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--structures", type=int, default=2000)
-ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--mode", default="f16x3")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)

@@ -54,7 +54,7 @@ def run(name, tag, n, n_struct, mode):
 
 
 if __name__ == "__main__":
-    mode = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+    mode = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
     run("configs[2]: i_v4_0, 32 x 8192 synthetic atoms, one batch", "i_v4_0", 8192, 32, mode)
     run("configs[3]: i_v4_1, one synthetic chain of 32768 atoms", "i_v4_1", 32768, 1, mode)
     run("configs[0]-sized: i_v4_1, one structure of 2386 atoms (launch-bound regime)", "i_v4_1", 2386, 1, mode)

@@ -14,5 +14,5 @@ if [ "$3" == "no-ncu" ]; then exit 0; fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1; echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:edge_kernel_tc -c 1 -s 31 -f -o $out/${tag}_edge64 \
-    python profiles/run_forward.py --atoms 32768 --mode bf16x3 > $out/${tag}_ncu_full.log 2>&1; echo "ncu full exit $?"
+    python profiles/run_forward.py --atoms 32768 --mode f16x3 > $out/${tag}_ncu_full.log 2>&1; echo "ncu full exit $?"
 ncu -i $out/${tag}_edge64.ncu-rep --page details > $out/${tag}_edge64_details.txt 2>&1

@@ -14,7 +14,7 @@ from pesto_b200.synth import synth_structure, one_hot_features       # noqa: E40
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--atoms", type=int, default=32768)
-ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--mode", default="f16x3")
 ap.add_argument("--tiles", type=int, default=48)
 a = ap.parse_args()
 g = os.path.join(REPO, "tests", "golden")

@@ -369,23 +369,27 @@ def test_tensor_core_layer_against_fp32_layer(cuda_models, mode, tol):
 
 @pytest.mark.parametrize("name,tag", [("2CUA_A", "i_v4_1"), ("1gpw_A", "i_v4_1"), ("tiny40", "i_v4_1"),
                                       ("batch3", "i_v4_0"), ("synth517", "i_v4_1"), ("1EWY", "i_v4_1")])
-def test_logits_bf16x3_within_north_star_tolerance(cuda_models, name, tag):
-    """Parity mode on the tensor cores: 3-term split bf16, logits within 1e-3 of the reference."""
+def test_logits_f16x3_within_north_star_tolerance(cuda_models, name, tag):
+    """Parity mode on the tensor cores (default mode): 3-term split product over fp16 hi/lo planes.  The north_star bar is
+    1e-3 on the logits; the fp16 planes measure ~1e-4 (bf16 planes: 5e-4 .. 7.5e-4), so a regression to bf16-plane accuracy
+    fails here (3e-4) long before the bar is at risk.  The former mode name is an alias."""
     c = load_case(name)
-    z = run_case(cuda_models(tag), c, mode="bf16x3").cpu()
+    z = run_case(cuda_models(tag), c, mode="f16x3").cpu()
     err = (z - torch.from_numpy(c[f"z_{tag}"])).abs().max().item()
-    assert err <= LOGIT_TOL, err
+    assert err <= LOGIT_TOL and err <= 3e-4, err
+    assert torch.equal(z, run_case(cuda_models(tag), c, mode="bf16x3").cpu())
 
 
-def test_logits_bf16_speed_mode_reports_its_error(cuda_models):
-    """Single-pass bf16 cannot meet 1e-3 (~0.14 on logits); it must stay a sane approximation."""
+def test_logits_f16_speed_mode_reports_its_error(cuda_models):
+    """A single 16-bit pass cannot meet 1e-3 (tf32-like operands ~0.025 on logits, bf16 ~0.14; fp16 planes
+    measure ~0.025); it must stay a sane approximation."""
     c = load_case("2CUA_A")
-    z = run_case(cuda_models("i_v4_1"), c, mode="bf16").cpu()
+    z = run_case(cuda_models("i_v4_1"), c, mode="f16").cpu()
     ref = torch.from_numpy(c["z_i_v4_1"])
     err = (z - ref).abs().max().item()
     perr = (torch.sigmoid(z) - torch.sigmoid(ref)).abs().max().item()
-    print(f"bf16 speed mode: max|dz| = {err:.3e}, max|dp| = {perr:.3e}")
-    assert err < 1.0 and perr < 0.1
+    print(f"f16 speed mode: max|dz| = {err:.3e}, max|dp| = {perr:.3e}")
+    assert err < 0.2 and perr < 0.03
 
 
 def test_config4_large_chain_32768(cuda_models):
