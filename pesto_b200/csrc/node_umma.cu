@@ -122,7 +122,14 @@ __device__ __forceinline__ float n_elu(float x) {
     return (x - n) + (e - 1.0f);
 }
 
-// (a, b) -> bf16x2 hi word and, if SPLIT, the bf16x2 word of the remainders
+// |p| feeds 16-bit operand planes only (the state record keeps p itself): one MUFU.SQRT (<= 1 ulp) instead of the IEEE
+// sequence with its slow-path call
+__device__ __forceinline__ float n_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// (a, b) -> 16-bit x2 hi word and, if SPLIT, the word of the remainders
 template <bool SPLIT>
 __device__ __forceinline__ void nsplit(float a, float b, uint32_t &hi, uint32_t &lo) {
     if (SPLIT) tc::split_h16x2(a, b, hi, lo);
@@ -204,7 +211,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
     tc::fence_after_sync();
     const int warp_u = __shfl_sync(FULLM, warp, 0);
     const uint32_t tbase = __shfl_sync(FULLM, *tmem_slot, 0);
-    const uint32_t tq = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tq = tbase + ((uint32_t)(warp_u * 32) << 16);     // warp-uniform: TMEM addresses stay in uniform registers
     const uint32_t sb = tc::smem_u32(smem_raw);
     uint32_t pa = 0, pb = 0;
     bool alive = true;
@@ -417,8 +424,8 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                 store_a8<SPLIT>(tq + A0 + 8 * g, tq + A0 + 32 + 8 * g, hi, lo);                 // q: K positions 0..31
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    nsplit<SPLIT>(sqrtf(pn2[k][0]), sqrtf(pn2[k][1]), hi[k][0], lo[k][0]);       // |p| (:105)
-                    nsplit<SPLIT>(sqrtf(pn2[k][2]), sqrtf(pn2[k][3]), hi[k][1], lo[k][1]);
+                    nsplit<SPLIT>(n_sqrt(pn2[k][0]), n_sqrt(pn2[k][1]), hi[k][0], lo[k][0]);     // |p| (:105)
+                    nsplit<SPLIT>(n_sqrt(pn2[k][2]), n_sqrt(pn2[k][3]), hi[k][1], lo[k][1]);
                 }
                 store_a8<SPLIT>(tq + A0 + 16 + 8 * g, tq + A0 + 48 + 8 * g, hi, lo);           // |p|: K positions 32..63
             }

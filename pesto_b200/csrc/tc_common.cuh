@@ -292,7 +292,13 @@ __device__ __forceinline__ void split_h16x2(float a, float b, uint32_t &hi, uint
     hi = pack_h16x2(a, b);
     float ha, hb;
     unpack_h16x2(hi, ha, hb);
-    lo = pack_h16x2(a - ha, b - hb);
+    unsigned long long x, h, l;                       // one packed subtract (FADD2) for the two remainders
+    asm("mov.b64 %0, {%1,%2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(h) : "f"(-ha), "f"(-hb));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(l) : "l"(x), "l"(h));
+    float la, lb;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(la), "=f"(lb) : "l"(l));
+    lo = pack_h16x2(la, lb);
 }
 
 }  // namespace tc
