@@ -9,7 +9,7 @@ BASELINE configs[1], the 53 `pdbs_test` structures (132 417 atoms, 16 632 residu
 (src/dataset.py:91-112 semantics, sparse membership).  Every rank processes the full workload (weak scaling).
 
   value     forward only, inputs (X, ids_topk, q0, residue index) resident in HBM, CUDA events, max over ranks
-  e2e       per step: pinned host X/q0/residue-index -> device, kNN topology on the device, forward, logits -> host
+  e2e       per step: pinned host X / element index / residue index -> device, kNN topology on the device, forward, logits -> host
   roofline  the fused per-edge StateUpdate kernel of the nn=64 layers: algorithmic bytes N*(64*536+1024) / measured
             kernel time (CUDA events on the launching stream) vs the measured HBM peak of MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (torch, all host threads) on a bounded sample (one structure of the workload)
@@ -217,9 +217,12 @@ def main():
 
     zbuf = torch.empty((n_res, 5), dtype=torch.float32).pin_memory()
 
+    elh = wl["el"].to(torch.uint8).pin_memory()       # element column per atom: one byte over PCIe instead of the 30-float
+                                                      # one-hot row, which is expanded on the device (as pesto_b200.runner does)
+
     def step_e2e():
         X = Xh.to(dev, non_blocking=True)
-        q0 = q0h.to(dev, non_blocking=True)
+        q0 = torch.nn.functional.one_hot(elh.to(dev, non_blocking=True).long(), q0h.shape[1]).to(torch.float32)
         rid = ridh.to(dev, non_blocking=True)
         ids = batch_topology(X, sizes, 64)
         z = model(X, ids, q0, rid, n_res=n_res)
@@ -330,9 +333,9 @@ def main():
                        "l2": "no flush needed: per-step working set (state 136 MB + geometry 136 MB + node factors 348 MB) exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": total_atoms * args.steps / (ms_e2e * 1e-3), "unit": "atoms/s",
-                    "h2d_bytes_per_step": int(Xh.numel() * 4 + q0h.numel() * 4 + ridh.numel() * 4),
+                    "h2d_bytes_per_step": int(Xh.numel() * 4 + elh.numel() + ridh.numel() * 4),
                     "d2h_bytes_per_step": int(zbuf.numel() * 4), "ms_per_step": ms_e2e / args.steps,
-                    "includes": "pinned H2D of X/q0/residue index, kNN topology (3 launches), forward, D2H of logits",
+                    "includes": "pinned H2D of X / element index (uint8, one-hot expanded on the device) / residue index, kNN topology (3 launches), forward, D2H of logits",
                     "logits_equal_resident_run": same},
             "gpu_launches": int(launches_fwd * args.steps),
             "roofline": roof,

@@ -64,6 +64,9 @@ def extract_topology(X, num_nn):
     and R are never built; no caller of the reference reads them, so they are returned as None.
     CPU tensors are staged through the GPU (results come back on X's device); without CUDA this raises.
     """
+    if X.dim() != 2 or X.shape[1] != 3 or X.shape[0] == 0:
+        # the reference fails on an empty structure as well (torch.max of an empty tensor, src/data_encoding.py:93)
+        raise ValueError(f"extract_topology: X must be [N, 3] with N >= 1, got {tuple(X.shape)}")
     if not torch.cuda.is_available():
         raise _lib.PestoError("extract_topology needs a CUDA device: there is no CPU implementation")
     if num_nn > 64:

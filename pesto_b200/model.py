@@ -160,6 +160,8 @@ class Model(torch.nn.Module):
         if Xd.dim() != 2 or Xd.shape[1] != 3 or ids.dim() != 2 or qd.dim() != 2 or \
                 ids.shape[0] != Xd.shape[0] or qd.shape[0] != Xd.shape[0]:
             raise ValueError(f"bad input shapes X{tuple(Xd.shape)} ids_topk{tuple(ids.shape)} q0{tuple(qd.shape)}")
+        if Xd.shape[0] == 0:
+            raise ValueError("Model.forward: empty structure (0 atoms)")
         if qd.shape[1] != self.config["em"]["N0"]:
             raise ValueError(f"q0 has {qd.shape[1]} features, the model expects {self.config['em']['N0']}")
         n_atoms = Xd.shape[0]

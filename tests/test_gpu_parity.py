@@ -81,7 +81,7 @@ def test_knn_duplicate_atoms_and_tiny_structures():
     X, _, _ = synth_structure(200, 11)
     X[17] = X[3]                     # exact duplicate
     X[50] = X[51] + 0.004            # closer than the 1e-2 mask
-    for n in (200, 66, 65, 64, 2):
+    for n in (200, 66, 65, 64, 2, 1):
         Xn = X[:n].contiguous()
         ids, d, r, _, _ = extract_topology(Xn.cuda(), 64)
         oi, od, orr = O.extract_topology(Xn, 64)
@@ -321,6 +321,8 @@ def test_bad_inputs_raise_or_poison(cuda_models):
     M2[3] = 0.0                                                    # not one-hot -> NaN logits
     assert torch.isnan(model(X.cuda(), ids, q0, M2)).all()
     assert torch.isfinite(model(X.cuda(), ids, q0, M)).all()       # and the model still works afterwards
+    with pytest.raises(ValueError):                                # empty structure: the reference raises too (max of empty)
+        model(X[:0].cuda(), ids[:0], q0[:0], M[:0])
 
 
 # ------------------------------------------------------------------------------------------------- tensor-core modes

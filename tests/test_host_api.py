@@ -136,3 +136,13 @@ def test_runner_packing_and_encoding():
     els = np.array(list(std_elements) + ["X", "", "Zz", "H", "c"])
     assert list(element_index(els)) == list(onehot(els, std_elements).argmax(1))
     assert list(encode_batch([a, b], as_index=True)[1]) == [0, 2, 29, 1, 3, 0]
+
+
+def test_empty_structure_is_rejected_before_any_device_work():
+    import pytest
+    import torch
+    from pesto_b200.data_encoding import extract_topology
+    with pytest.raises(ValueError):
+        extract_topology(torch.zeros((0, 3)), 64)
+    with pytest.raises(ValueError):
+        extract_topology(torch.zeros((5, 2)), 64)
