@@ -132,6 +132,11 @@ def reference_arm(args, rank):
     wl = load_workload()
     weights = load_weights()
     sample = cpu_sample(wl)
+    # bounded sample: time one structure, then keep as many of the 16 as fit ~150 s over all warm-up + timed steps
+    ids_probe, _ = cpu_topology(sample[:1])
+    t_probe, _ = cpu_forward_seconds(weights, sample[:1], ids_probe)
+    n_keep = max(2, min(len(sample), int(150.0 / (max(args.steps + args.warmup, 1) * max(t_probe, 1e-3)))))
+    sample = sample[:n_keep]
     ids1, t_knn = cpu_topology(sample)
     for _ in range(args.warmup):
         cpu_forward_seconds(weights, sample, ids1)
