@@ -88,15 +88,23 @@ __device__ __forceinline__ void scan_range(TopK &t, float &rowmax, const float *
 template <int MODE>
 __device__ __forceinline__ void scan_segment(TopK &t, float &rowmax, const float *__restrict__ X, int lo, int hi, int i,
                                              float xi, float yi, float zi, float maxd, int lane) {
-    // chain-ordered structures have most neighbours close in index: scan a window around i first so
-    // that the threshold tightens early, then the rest.
-    constexpr int W = 256;
-    int wa = max(lo, ((i - W) / 32) * 32);
-    if (i - W < lo) wa = lo;
-    int wb = min(hi, wa + 2 * W + 32);
-    scan_range<MODE>(t, rowmax, X, lo, wa, wb, xi, yi, zi, maxd, lane);
-    scan_range<MODE>(t, rowmax, X, lo, lo, wa, xi, yi, zi, maxd, lane);
-    scan_range<MODE>(t, rowmax, X, lo, wb, hi, xi, yi, zi, maxd, lane);
+    // chain-ordered structures have most neighbours close in index: scan outwards from i in 64-atom steps (both sides
+    // alternately) so that the list fills with near-final entries and the threshold tightens early -- every later
+    // candidate that passes costs a warp-wide insertion -- then the rest of the structure
+    constexpr int W = 256, STEP = 64;
+    const int c0 = max(lo, (i / 32) * 32 - 32);            // first block: [c0, c0 + 96) contains i
+    int left = c0, right = min(hi, c0 + 96);
+    scan_range<MODE>(t, rowmax, X, lo, left, right, xi, yi, zi, maxd, lane);
+#pragma unroll 1
+    for (int s = 0; s < W / STEP; ++s) {
+        const int nl = max(lo, left - STEP), nr = min(hi, right + STEP);
+        if (nl < left) scan_range<MODE>(t, rowmax, X, lo, nl, left, xi, yi, zi, maxd, lane);
+        if (nr > right) scan_range<MODE>(t, rowmax, X, lo, right, nr, xi, yi, zi, maxd, lane);
+        left = nl;
+        right = nr;
+    }
+    scan_range<MODE>(t, rowmax, X, lo, lo, left, xi, yi, zi, maxd, lane);
+    scan_range<MODE>(t, rowmax, X, lo, right, hi, xi, yi, zi, maxd, lane);
 }
 
 __device__ __forceinline__ void write_row(const TopK &t, const float *__restrict__ X, int i, int lo, int n, int k,
