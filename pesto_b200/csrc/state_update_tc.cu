@@ -504,26 +504,33 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         tc::wait_st();
         tc::fence_before_sync();
     };
+    // M1: D1 (X) = A1 . B1^T, K = 80, split by accumulator columns over M1S issuing warps (each a chain over 128 / M1S
+    // columns with its own chunk commits).  An issuing warp is held back while the tensor-core queue drains -- and M1 is the
+    // longest chain (0.9 k cycles) -- so one issuer arrives that much later at the reduction's barrier than the other seven
+    // warps; four issuers (warps 0, 2, 4, 6) are held back a quarter as long (+1.9 %; at nn = 8 one issuer measures better)
+    constexpr int M1S = NN >= 16 ? 4 : 1;
     auto issue_m1 = [&]() {
-        if (hwarp_u == 0 && tc::elect_one()) {                           // M1: D1 (X) = A1 . B1^T, K = 80
+        constexpr int NC = 128 / M1S;                                   // columns per issuer
+        if ((hwarp_u % (8 / M1S)) == 0 && tc::elect_one()) {
+            const uint32_t c = M1S == 1 ? 0u : (uint32_t)hwarp_u / (8 / M1S);      // column block of this issuer
             tc::fence_after_sync();
-            constexpr uint32_t idesc = tc::idesc_h16(128, 128);
+            constexpr uint32_t idesc = tc::idesc_h16(128, NC);
             constexpr uint32_t lbo = 128u * 16u;
+            const uint32_t r14 = c * NC;                                 // rows NC c .. of every K group, in 16-byte units
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                const uint64_t dh = s < 4 ? tc::smem_desc14(img14, tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u)
-                                          : tc::smem_desc14(ext14, 0u, lbo, 128u);
-                tc::umma_ts(tbase + TX, tbase + TY + 8u * s, dh, idesc, s > 0);
+                const uint64_t dh = s < 4 ? tc::smem_desc14(img14 + r14, tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u)
+                                          : tc::smem_desc14(ext14 + r14, 0u, lbo, 128u);
+                tc::umma_ts(tbase + TX + c * NC, tbase + TY + 8u * s, dh, idesc, s > 0);
                 if (SPLIT) {
-                    tc::umma_ts(tbase + TX, tbase + TY + 40u + 8u * s, dh, idesc, 1u);
+                    tc::umma_ts(tbase + TX + c * NC, tbase + TY + 40u + 8u * s, dh, idesc, 1u);
                     if (s < 4)
-                        tc::umma_ts(tbase + TX, tbase + TY + 8u * s,
-                                    tc::smem_desc14(img14, tcimg::IMG + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
+                        tc::umma_ts(tbase + TX + c * NC, tbase + TY + 8u * s,
+                                    tc::smem_desc14(img14 + r14, tcimg::IMG + tcimg::B1 + (uint32_t)s * 2u * lbo, lbo, 128u), idesc, 1u);
                 }
             }
-            // (full-width MMAs: N = 32 column chunks with separate commits measured slower at nn = 64)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tc::umma_commit(bars_u + c);
+            for (int q = 0; q < 4 / M1S; ++q) tc::umma_commit(bars_u + c * (4 / M1S) + q);      // chunk barriers of these columns
         }
     };
     // E-stage register mapping (16x256b): this thread owns the rows 8 k + rl (k < 4) of its warp's 32 edges and, in a
