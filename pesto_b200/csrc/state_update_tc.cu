@@ -395,7 +395,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     // and the U_i values; s0_store: words -> TMEM (Y), [d, 1(a), d] columns, U planes -> B1's spare K rows.  S0 runs one
     // tile AHEAD (after E3 of the previous tile, when Y is free again), so that the first-layer MMA of a tile executes
     // while the reduction phase R of the previous tile occupies the CUDA cores.
-    uint32_t s0h[16], s0l[16];
+    // nn = 64: the p_j . r gather of a tile is shared by the two column groups (one gather round trip each instead of two on
+    // the group that also computes the attention weights): -2 % there; at nn <= 32 the extra live words spill and it loses
+    constexpr bool S0SPLIT = NN == 64;
+    uint32_t s0h[16], s0l[16];          // group 0 (!S0SPLIT): p_j . r words of all four row groups; group 1: p_i . r words
+    uint32_t s0ph[8], s0pl[8];          // S0SPLIT: p_j . r words of this thread's two row groups (group g: 2g, 2g + 1)
     float u0v[UMMA ? TA : 1];
     auto s0_compute = [&](int tile, int j, const float4 &g) {
         if (UMMA && grp == 1) {      // U_i of the tile's atoms (group 1 has the lighter S0)
@@ -406,7 +410,30 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 u0v[m] = __ldg(nodeC + (size_t)(ia + 1) * NODE_C_STRIDE + col_channel(v & 127));    // column n holds channel col_channel(n)
             }
         }
-        if (grp == 0) {
+        if (S0SPLIT) {
+            // both groups: rows 8 (2 grp + q) + lane / 4, q < 2, of the warp's 32 edges (see the 4-row-group version below)
+            float x[2][8], y[2][8], z[2][8];
+            u64 kx[2], ky[2], kz[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int sl = 8 * (2 * grp + q) + (lane >> 2);
+                const int jk = __shfl_sync(FULLM, j, sl);
+                const float rx = __shfl_sync(FULLM, g.x, sl), ry = __shfl_sync(FULLM, g.y, sl), rz = __shfl_sync(FULLM, g.z, sl);
+                kx[q] = pk2(rx, rx); ky[q] = pk2(ry, ry); kz[q] = pk2(rz, rz);
+                const float *sJk = state_in + (size_t)jk * SR + 32 + 8 * (lane & 3);
+                tc::ldg256(sJk, x[q]);
+                tc::ldg256(sJk + 32, y[q]);
+                tc::ldg256(sJk + 64, z[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const u64 pr = fma2(kz[q], pk2(z[q][2 * u], z[q][2 * u + 1]),
+                                        fma2(ky[q], pk2(y[q][2 * u], y[q][2 * u + 1]), mul2(kx[q], pk2(x[q][2 * u], x[q][2 * u + 1]))));
+                    split2<SPLIT>(pr, kc, s0ph[4 * q + u], s0pl[4 * q + u]);     // [row group q][word u]
+                }
+        } else if (grp == 0) {
             // p_j . r through the 16x256b store shape: four neighbouring lanes share an edge row and read one 128-byte
             // line of p_j per component (8 lines per load instruction instead of 32); each thread covers the rows
             // 8k + lane/4 (k < 4) of its warp's 32 edges and the channels 8m .. 8m+7, m = lane % 4
@@ -434,7 +461,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             dot_rows(0); dot_rows(1);
             gather_rows(2); gather_rows(3);
             dot_rows(2); dot_rows(3);
-        } else {
+        } else if (!S0SPLIT) {
             const float *src = state_in + (size_t)(min(tile * TA + a_loc, n_atoms - 1) + 1) * SR;
             const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
 #pragma unroll
@@ -451,11 +478,23 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
         }
     };
-    auto s0_store = [&](const float4 &g) {
+    // S0SPLIT: p_j . r words -> TMEM (Y), 16 rows of the warp's quarter per group.  Group 0 stores with the rest of S0 (after
+    // the attention stage), group 1 as soon as every MMA of M3 has read Y (in the middle of its V copy), which frees its registers
+    auto s0_store_pj = [&]() {
+        const uint32_t ta = tlane + ((uint32_t)(16 * grp) << 16) + TY;
+        const uint32_t h8[8] = {s0ph[0], s0ph[1], s0ph[4], s0ph[5], s0ph[2], s0ph[3], s0ph[6], s0ph[7]};
+        tc::tmem_st_16x256b_x2(ta, h8);
+        if (SPLIT) {
+            const uint32_t l8[8] = {s0pl[0], s0pl[1], s0pl[4], s0pl[5], s0pl[2], s0pl[3], s0pl[6], s0pl[7]};
+            tc::tmem_st_16x256b_x2(ta + 40, l8);
+        }
+    };
+    auto s0_store = [&](int tile, const float4 &g) {
         // hi: Y + [0,16) p_j.r, [16,32) p_i.r, [32,40) d + U indicator columns;  lo: Y + 40 + same.
         if (grp == 0) {
+            if (S0SPLIT) s0_store_pj();
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
+            for (int hb = 0; hb < (S0SPLIT ? 0 : 2); ++hb) {
                 const uint32_t ta = tlane + ((uint32_t)(16 * hb) << 16) + TY;
                 const uint32_t h8[8] = {s0h[8 * hb + 0], s0h[8 * hb + 1], s0h[8 * hb + 4], s0h[8 * hb + 5],
                                         s0h[8 * hb + 2], s0h[8 * hb + 3], s0h[8 * hb + 6], s0h[8 * hb + 7]};
@@ -467,6 +506,23 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 }
             }
         } else {
+            if (S0SPLIT) {     // p_i . r (rows of the centre atom: L1 hits), computed next to its only use so that the words are
+                               // not held across the V copy
+                const float *src = state_in + (size_t)(min(tile * TA + a_loc, n_atoms - 1) + 1) * SR;
+                const u64 gx = pk2(g.x, g.x), gy = pk2(g.y, g.y), gz = pk2(g.z, g.z);
+#pragma unroll
+                for (int sc = 0; sc < S; sc += 8) {
+                    float x[8], y[8], z[8];
+                    tc::ldg256(src + 32 + sc, x);
+                    tc::ldg256(src + 64 + sc, y);
+                    tc::ldg256(src + 96 + sc, z);
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        const u64 pr = fma2(gz, pk2(z[u], z[u + 1]), fma2(gy, pk2(y[u], y[u + 1]), mul2(gx, pk2(x[u], x[u + 1]))));
+                        split2<SPLIT>(pr, kc, s0h[(sc + u) >> 1], s0l[(sc + u) >> 1]);
+                    }
+                }
+            }
             tc::tmem_st16(tlane + TY + 16, s0h);
             if (SPLIT) tc::tmem_st16(tlane + TY + 40 + 16, s0l);
             {
@@ -557,7 +613,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #endif
         {
             s0_compute(tile0, j_next, g_next);
-            s0_store(g_next);
+            if (S0SPLIT && grp != 0) s0_store_pj();
+            s0_store(tile0, g_next);
             if (TPREF) {
                 load_T(j_next, 0);
 #ifdef PESTO_X_TPREF2B
@@ -793,7 +850,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int half = 0; half < 2; ++half) {
                 if (half == 1) {
                     if (alive) alive = tc::mbar_wait(bar1, ph1, &g_tc_watchdog, 3);
+                    if (S0SPLIT && alive) alive = tc::mbar_wait(bars + 1, ph1, &g_tc_watchdog, 3);      // ... and Kq | Kp: Y is free
                     tc::fence_after_sync();
+                    if (S0SPLIT) s0_store_pj();
                 }
 #pragma unroll
                 for (int q16 = 0; q16 < 2; ++q16) {
@@ -819,7 +878,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             // every MMA of M3 has read Y: each group has waited for its own GEMMs, now for the other group's last commit
             if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, &g_tc_watchdog, 3);
             tc::fence_after_sync();
-            s0_store(gn);
+            s0_store(tile + tstride, gn);
         }
         // p_j of the reduction group's 8 edges (phase R): issued before the barrier so that part of the gather latency overlaps it
 #ifndef PESTO_X_PJR2
