@@ -22,6 +22,8 @@ from .structure_io import save_pdb
 
 def load_model(model_dir, checkpoint="model_ckpt.pt", mode="f16x3", device="cuda"):
     """Model(config_model) + load_state_dict of the shipped checkpoint (apply_model.ipynb cells 2-4)."""
+    from . import compat
+    compat.install()          # the reference's config.py imports `src.data_encoding` at module level
     spec = importlib.util.spec_from_file_location("pesto_reference_config", os.path.join(model_dir, "config.py"))
     cfg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(cfg)

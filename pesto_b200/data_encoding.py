@@ -19,6 +19,20 @@ std_names = np.array(("CA N C O CB CG CD2 CD1 CG1 CG2 CD OE1 OE2 OG OG1 OD1 OD2 
                       "N7 C8 N1 N3 C2 C4 C6 C5 N6 N4 O2 O4").split())
 config_encoding = {"std_elements": std_elements, "std_resnames": std_resnames, "std_names": std_names}
 
+# residue-name categories of the five interface types (src/data_encoding.py:32-46): a vocabulary the reference's own
+# config.py imports at module level (`from src.data_encoding import categ_to_resnames`), so it has to exist for
+# `from config import config_model` to run under pesto_b200.compat; the forward path never reads it
+categ_to_resnames = {
+    "protein": "GLU LEU ALA ASP SER VAL GLY THR ARG PHE TYR ILE PRO ASN LYS GLN HIS TRP MET CYS".split(),
+    "rna": "A U G C".split(),
+    "dna": "DA DT DG DC".split(),
+    "ion": "MG ZN CL CA NA MN K IOD CD CU FE NI SR BR CO HG".split(),
+    "ligand": ("SO4 NAG PO4 EDO ACT MAN HEM FMT BMA ADP FAD NAD NO3 GLC ATP NAP BGC GDP FUC FES FMN GAL GTP PLP MLI "
+               "ANP H4B AMP NDP SAH OXY").split(),
+    "lipid": "PLM CLR CDL RET".split(),
+}
+resname_to_categ = {rn: c for c, names in categ_to_resnames.items() for rn in names}
+
 
 def onehot(x, v):
     """[len(x), len(v)+1] bool: membership in vocabulary v, last column = not in v (src/data_encoding.py:56-58)."""

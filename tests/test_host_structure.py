@@ -128,3 +128,18 @@ def test_encode_bfactor_and_compat_imports():
     from model import Model                                                                    # noqa: F401
     with pytest.raises(NotImplementedError):
         select_by_sid(None, None)
+
+
+REF_MODEL_DIR = "/root/reference/model/save/i_v4_1_2021-09-07_11-21"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_MODEL_DIR, "model_ckpt.pt")), reason="reference checkout not present")
+def test_load_model_from_the_reference_checkout():
+    """apply_model.ipynb cells 2-4 against the reference's own files: its config.py (which imports src.data_encoding at module
+    level) and the shipped checkpoint load strictly into pesto_b200.Model (1 474 957 parameters, SURVEY.md section 2.1 #7)."""
+    from pesto_b200.apply import load_model
+    from pesto_b200.data_encoding import categ_to_resnames, resname_to_categ
+    model = load_model(REF_MODEL_DIR, device="cpu")
+    assert sum(p.numel() for p in model.parameters()) == 1474957
+    assert len(model.config["sum"]) == 32 and model.mode == "f16x3"
+    assert resname_to_categ["ZN"] == "ion" and len(categ_to_resnames["protein"]) == 20 and len(resname_to_categ) == 79
