@@ -34,6 +34,11 @@ def install():
             setattr(dataset, name, _out_of_scope(name))
     if not hasattr(structure, "data_to_structure"):
         structure.data_to_structure = _out_of_scope("data_to_structure")
+    scoring = types.ModuleType("src.scoring")             # src/scoring.py: evaluation metrics (imported by the notebooks' first cell)
+    scoring.bc_score_names = ["acc", "ppv", "npv", "tpr", "tnr", "mcc", "auc", "std"]
+    for name in ("bc_scoring", "nanmean", "acc", "ppv", "npv", "tpr", "tnr", "mcc", "roc_auc"):
+        setattr(scoring, name, _out_of_scope("src.scoring." + name))
+    mods["src.scoring"] = scoring
     handler = types.ModuleType("data_handler")            # model/save/*/data_handler.py: HDF5 training dataset
     handler.Dataset = _out_of_scope("data_handler.Dataset")
     mods["data_handler"] = handler

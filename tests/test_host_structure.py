@@ -126,6 +126,8 @@ def test_encode_bfactor_and_compat_imports():
     from src.structure import data_to_structure, encode_bfactor as eb, concatenate_chains      # noqa: F401
     from src.structure_io import save_pdb, read_pdb                                            # noqa: F401
     from model import Model                                                                    # noqa: F401
+    from src.scoring import bc_scoring, bc_score_names                                         # noqa: F401  (apply_model.ipynb:25)
+    assert len(bc_score_names) == 8
     with pytest.raises(NotImplementedError):
         select_by_sid(None, None)
 
