@@ -145,3 +145,36 @@ def test_load_model_from_the_reference_checkout():
     assert sum(p.numel() for p in model.parameters()) == 1474957
     assert len(model.config["sum"]) == 32 and model.mode == "f16x3"
     assert resname_to_categ["ZN"] == "ion" and len(categ_to_resnames["protein"]) == 20 and len(resname_to_categ) == 79
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_MODEL_DIR, "model_ckpt.pt")), reason="reference checkout not present")
+def test_apply_notebook_cells_run_unchanged_up_to_the_device_call(monkeypatch):
+    """apply_model.ipynb cells 0 and 2-6 (the lines that touch this path), executed as written after compat.install(): imports,
+    `from config import config_model` from the reference's model directory, Model + load_state_dict, StructuresDataset,
+    encoding -- and extract_topology either runs (GPU) or fails loudly (no GPU): there is no CPU fallback."""
+    import sys
+    import torch as pt
+    import pesto_b200.compat as compat
+    from pesto_b200 import _lib
+    compat.install()
+    monkeypatch.syspath_prepend(REF_MODEL_DIR)
+    sys.modules.pop("config", None)
+    from src.dataset import StructuresDataset, collate_batch_features                          # noqa: F401
+    from src.data_encoding import encode_structure, encode_features, extract_topology
+    from src.structure import concatenate_chains
+    from config import config_model
+    from model import Model
+    model = Model(config_model)
+    assert str(model.load_state_dict(pt.load(os.path.join(REF_MODEL_DIR, "model_ckpt.pt"), map_location=pt.device("cpu")))) \\
+        == "<All keys matched successfully>"
+    model = model.eval().to(pt.device("cpu"))
+    fp = "/root/reference/examples/issue_19_04_2023/2CUA_A.pdb"
+    subunits, filepath = StructuresDataset([fp], with_preprocessing=True)[0]
+    structure = concatenate_chains(subunits)
+    X, M = encode_structure(structure)
+    q = encode_features(structure)[0]
+    assert X.shape == (955, 3) and M.shape == (955, 122) and q.shape == (955, 30)
+    if not pt.cuda.is_available():
+        with pytest.raises(_lib.PestoError):
+            extract_topology(X, 64)
+    sys.modules.pop("config", None)
