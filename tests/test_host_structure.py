@@ -165,8 +165,8 @@ def test_apply_notebook_cells_run_unchanged_up_to_the_device_call(monkeypatch):
     from config import config_model
     from model import Model
     model = Model(config_model)
-    assert str(model.load_state_dict(pt.load(os.path.join(REF_MODEL_DIR, "model_ckpt.pt"), map_location=pt.device("cpu")))) \\
-        == "<All keys matched successfully>"
+    res = model.load_state_dict(pt.load(os.path.join(REF_MODEL_DIR, "model_ckpt.pt"), map_location=pt.device("cpu")))
+    assert str(res) == "<All keys matched successfully>"
     model = model.eval().to(pt.device("cpu"))
     fp = "/root/reference/examples/issue_19_04_2023/2CUA_A.pdb"
     subunits, filepath = StructuresDataset([fp], with_preprocessing=True)[0]
