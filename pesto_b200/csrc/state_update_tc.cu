@@ -4,11 +4,15 @@
 // pipelines ("halves") sharing one copy of the weight images; inside a half, thread t and thread t+128 both map to
 // edge t % 128 <-> TMEM lane t % 128 and split the columns of every stage.  Per tile:
 //
-//   S0   gather p_j; A1 = [p_j.r (32) | p_i.r (32) | d, 1(atom) (16)] as bf16 (hi | lo) -> TMEM      (CUDA cores)
-//        U_i (per-atom factor) as three bf16 planes -> spare K rows of B1 in shared memory (nn >= 32)
+//   S0   gather p_j; A1 = [p_j.r (32) | p_i.r (32) | d, 1(atom) (16)] as 16-bit (hi | lo) planes -> TMEM   (CUDA cores)
+//        U_i (per-atom factor) as three 16-bit planes -> spare K rows of B1 in shared memory (nn >= 32).
+//        S0 runs one tile AHEAD: its arithmetic under the third-layer MMA of the previous tile, its stores after that tile's
+//        E3 (nn = 64: the p_j gather is split between the two column groups)
 //   M1   D1[128x128] = A1 . B1^T,  B1 = [W1 cols of p_j.r ; p_i.r ; d ; U planes]                       (tcgen05.mma)
-//   E1   h1 = ELU(D1 + T_j)  (T_j: per-atom factor from the node kernel, gathered) -> A2 in place      (CUDA cores)
-//   M2   D2 = blockdiag(eqkm.2, epkm.2, evm.2) applied to A2's three column groups
+//        issued by four warps (32 accumulator columns each) after the previous tile's E3: it runs under that tile's R
+//   E1   h1 = ELU(D1 + T_j)  (T_j: per-atom factor from the node kernel, gathered from L2; for nn >= 32 the first
+//        chunk is loaded one tile ahead) -> A2 in place                                                  (CUDA cores)
+//   M2   D2 = blockdiag(eqkm.2, epkm.2, evm.2) applied to A2's three column groups (each group issues what it consumes)
 //   E2   h2 = ELU(D2 + b2) -> A3 in place
 //   M3   D3 = [eqkm.4 | epkm.4 | evm.4] applied to A3's column groups
 //   E3   group 0: logits, softmax over the atom's nn / 3nn tokens (warp shuffles) -> attention weights in smem;
@@ -18,9 +22,15 @@
 //
 // All pre-activations are carried scaled by log2(e) (folded into B1, b2, T, U on one side and 1/log2(e) into B3
 // on the other), so ELU needs a bare ex2 and no multiply.  The A operand of every MMA lives in TMEM (written by
-// tcgen05.st, thread-per-row, bf16 packed two per column), B (weights) in shared memory as K-major un-swizzled UMMA
+// tcgen05.st, 16-bit values packed two per column), B (weights) in shared memory as K-major un-swizzled UMMA
 // images prepared on the host at model-finalize time.  SPLIT = true computes hi*hi + lo*hi + hi*lo (3 MMAs per
-// K step, ~2^-17 relative error: parity mode); SPLIT = false is a single bf16 pass (speed mode).
+// K step) over fp16 planes (tc_common.cuh: ~2^-21 relative error, parity mode); SPLIT = false is a single pass (speed mode).
+//
+// Two rules this file follows because breaking them cost 10-17 % each time (profiles/README.md):
+//   * 512 threads x 128 registers is the whole register file: any value kept alive across a phase boundary spills;
+//   * a prefetch into a loop-carried array must be UNCONDITIONAL (load a valid dummy row when there is no next tile) and
+//     group-specific definitions / uses must test the SAME predicate: otherwise the old values stay live on the path
+//     the compiler cannot rule out, i.e. through the whole tile.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
