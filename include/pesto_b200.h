@@ -155,6 +155,16 @@ int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int 
  * int64) for the first max_tiles tiles of each half; buf == NULL switches it off. */
 int pesto_debug_edge_timeline(void *buf, int max_tiles);
 
+/* Debug: building blocks of the edge kernel's tensor-core reduction in isolation (csrc/rmma_probe.cu).  Gathers the
+ * 128 rows ids[] of p16 (device, fp16 [n_rows][192] = hi plane 96 | lo plane 96) with TMA tile::gather4 into
+ * shared memory and computes D[m][n] = sum_k (hi + lo)(ids[k], m) * W[n][k] (W: device fp32 [16][128]) as a 3-term
+ * split tcgen05.mma with both operands MN-major in shared memory -> D device fp32 [128][16] (rows >= 96 unspecified);
+ * Prec (device fp32 [128][96]) receives hi + lo of every gathered row as read back by threads from the swizzled tile,
+ * raw (optional, 48 KB) the tile's bytes.  a_/b_ lbo/sbo < 0 and idesc == 0 select the library's own descriptor values;
+ * *status (device int) receives a stage id if a wait timed out. */
+int pesto_debug_rmma_probe(const void *p16, int n_rows, const int32_t *ids, const float *W, float *D, float *Prec, void *raw,
+                           int a_lbo, int a_sbo, int b_lbo, int b_sbo, int idesc, int *status, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-side PDB text parser (no device work; every pointer is a HOST pointer).  Replaces the gemmi call inside
  * read_pdb                                                                  src/structure_io.py:6-55

@@ -133,9 +133,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // Bounded wait: a tensor-core stage that never completes must not hang the GPU.  On timeout the stage id is
 // recorded in *watchdog (global memory) and the caller carries on with garbage; hosts check the flag.
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *watchdog = nullptr, int stage = 0) {
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *watchdog = nullptr, int stage = 0,
+                                          uint32_t max_spin = 1u << 20) {
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 20); ++spin)
+    for (uint32_t spin = 0; spin < max_spin; ++spin)
         if (mbar_try_wait(bar, parity)) return true;
     if (watchdog) atomicMax(watchdog, stage);
     return false;

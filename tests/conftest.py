@@ -17,13 +17,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: long CPU oracle runs, opt in with PESTO_SLOW=1")
 
 
+def _gpu_unavailable():
+    if not torch.cuda.is_available():
+        return "no CUDA device"
+    from pesto_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        return f"{_lib.LIB_PATH} has not been built"
+    return None
+
+
 def pytest_collection_modifyitems(config, items):
-    if os.environ.get("PESTO_SLOW") == "1":
-        return
-    skip = pytest.mark.skip(reason="slow oracle run; set PESTO_SLOW=1")
+    why = _gpu_unavailable()
+    skip_gpu = pytest.mark.skip(reason=f"gpu test: {why}")
+    skip_slow = pytest.mark.skip(reason="slow oracle run; set PESTO_SLOW=1")
     for item in items:
-        if "slow" in item.keywords:
-            item.add_marker(skip)
+        if why and "gpu" in item.keywords:
+            item.add_marker(skip_gpu)
+        if "slow" in item.keywords and os.environ.get("PESTO_SLOW") != "1":
+            item.add_marker(skip_slow)
 
 
 def load_case(name):
@@ -61,15 +72,20 @@ def weights():
 
 @pytest.fixture(scope="session")
 def cuda_models():
-    """pesto_b200.Model instances on cuda:0 with the shipped checkpoints (from the golden weight fixtures)."""
+    """pesto_b200.Model instances on cuda:0 with the shipped checkpoints (from the golden weight fixtures).
+    `mode` is the instance's default arithmetic: "fp32" (FFMA kernels) or "f16x3" (tcgen05, the mode bench.py times)."""
     from pesto_b200.model import Model
     cache = {}
 
-    def get(tag):
-        if tag not in cache:
-            m = Model(load_config(tag), mode="fp32")      # tests pick tensor-core modes explicitly
+    def get(tag, mode="fp32"):
+        if (tag, mode) not in cache:
+            m = Model(load_config(tag), mode=mode)
             sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
             m.load_state_dict(sd)
-            cache[tag] = m.eval().to("cuda")
-        return cache[tag]
+            cache[(tag, mode)] = m.eval().to("cuda")
+        return cache[(tag, mode)]
     return get
+
+
+# the two arithmetic modes every size / property test runs in: the FFMA reference mode and the timed tensor-core mode
+BOTH_MODES = ["fp32", "f16x3"]

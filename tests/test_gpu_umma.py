@@ -67,3 +67,41 @@ def test_edge_timeline_debug_entry():
         model(Xd, ids1, q0, ridd, n_res=int(rid.max()) + 1)
     torch.cuda.synchronize()
     assert int(buf.abs().sum()) == 0
+
+
+def test_rmma_probe_gather4_and_mn_major_operands():
+    """TMA tile::gather4 (64-byte swizzle) of fp16 hi|lo neighbour records + tcgen05.mma with both operands MN-major
+    in shared memory (A = the records as they landed, B = per-edge weights written by threads): the building blocks
+    of the edge kernel's tensor-core reduction, against a float64 matmul."""
+    import os
+    import numpy as np
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    n_rows = 1000
+    p = torch.randn(n_rows, 96, generator=g) * 3
+    p[0] = 0
+    hi = p.half()
+    lo = (p - hi.float()).half()
+    p16 = torch.cat([hi, lo], 1).contiguous().cuda()
+    ids = torch.randint(0, n_rows, (128,), generator=g, dtype=torch.int32)
+    ids[5] = 0
+    ids[77] = n_rows - 1
+    W = torch.randn(16, 128, generator=g)
+    D = torch.full((128, 16), float("nan"), device="cuda")
+    Prec = torch.full((128, 96), float("nan"), device="cuda")
+    raw = torch.zeros(48 * 1024 // 4, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ids_d, W_d = ids.cuda(), W.cuda()                                  # (named: the pointers must outlive the call)
+    _lib.check(lib.pesto_debug_rmma_probe(p16.data_ptr(), n_rows, ids_d.data_ptr(), W_d.data_ptr(), D.data_ptr(),
+                                          Prec.data_ptr(), raw.data_ptr(), -1, -1, -1, -1, 0, status.data_ptr(), None), "rmma probe")
+    torch.cuda.synchronize()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        np.savez(os.path.join(out, "rmma_probe.npz"), D=D.cpu().numpy(), Prec=Prec.cpu().numpy(), raw=raw.cpu().numpy(),
+                 p16=p16.cpu().numpy().view(np.uint16), ids=ids.numpy(), W=W.numpy(), status=status.cpu().numpy())
+    assert int(status.item()) == 0, f"probe wait timed out at stage {int(status.item())}"
+    pg = (hi.double() + lo.double())[ids.long()]                       # [128 edges][96]
+    assert (Prec.cpu().double() - pg).abs().max().item() < 1e-6        # thread-side read of the swizzled tile
+    ref = pg.T @ W.double().T                                          # [96][16]
+    err = (D.cpu().double()[:96] - ref).abs().max().item()
+    assert err < 2e-5 * ref.abs().max().item(), err
