@@ -25,6 +25,8 @@ def predict_trajectory(model, X_traj, ids_topk, q, M, frames=None, frames_per_ba
     frames = list(range(n_frames)) if frames is None else list(frames)
     per = frames_per_batch or max(1, TARGET_ATOMS_PER_BATCH // max(n_atoms, 1))
     per = min(per, max(len(frames), 1))
+    if n_atoms < ids_topk.shape[1] or bool((ids_topk == 0).any()):
+        per = 1        # sink-padded neighbour slots read X[-1] of the batch (src/model_operations.py:8): one frame per forward
     dev = torch.device(device)
     ids = ids_topk.to(dev)
     rid = _residue_index(M.to(dev)).to(torch.int64)

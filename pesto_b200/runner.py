@@ -14,11 +14,20 @@ from .data_encoding import batch_topology, onehot, std_elements
 TARGET_ATOMS_PER_BATCH = 131072
 
 
-def pack_batches(sizes, target=TARGET_ATOMS_PER_BATCH):
+def pack_batches(sizes, target=TARGET_ATOMS_PER_BATCH, num_nn=64):
     """Greedy packing in the given order: lists of structure indices whose atom counts add up to <= target
-    (a structure larger than the target gets a batch of its own)."""
+    (a structure larger than the target gets a batch of its own).  So does a structure with fewer than num_nn atoms:
+    its neighbour lists are padded with sink slots, and a sink slot reads X[-1] -- the last atom of whatever the batch
+    holds (src/model_operations.py:8) -- so only alone does it get the numbers of the reference's one-structure-at-a-time
+    loop (interfaceome/apply_model.py:49-82)."""
     batches, cur, load = [], [], 0
     for i, n in enumerate(sizes):
+        if int(n) < num_nn:
+            if cur:
+                batches.append(cur)
+                cur, load = [], 0
+            batches.append([i])
+            continue
         if cur and load + int(n) > target:
             batches.append(cur)
             cur, load = [], 0
@@ -84,7 +93,7 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
     its pinned H2D copies on a copy stream while the GPU works, (3) the host waits for batch k's logits."""
     dev = torch.device(device)
     sizes = [len(s["xyz"]) for s in structures]
-    batches = pack_batches(sizes, target_atoms)
+    batches = pack_batches(sizes, target_atoms, num_nn)
     copy_stream = torch.cuda.Stream(dev)
     slots = [_PinnedSlot(), _PinnedSlot()]
 

@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, BOTH_MODES, load_weights
 
 pytestmark = pytest.mark.gpu
 PDB = os.path.join(GOLDEN, "pdb")
@@ -69,16 +69,22 @@ def test_apply_multichain_probabilities(tmp_path, cuda_models, name):
     assert max(abs(a - b) for a, b in zip(got, exp)) <= 0.0100001
 
 
-def test_trajectory_mode_equals_frame_by_frame(cuda_models):
+@pytest.mark.parametrize("mode,n_atoms", [("fp32", 700), ("f16x3", 700), ("f16x3", 48)])
+def test_trajectory_mode_equals_frame_by_frame(cuda_models, mode, n_atoms):
     """md_analysis/apply_model_md.ipynb cell 6: frame-0 topology reused for every frame; batching the frames as
-    structures gives the logits of the frame-by-frame loop (also with a partial last batch)."""
+    structures gives the logits of the frame-by-frame loop (also with a partial last batch) -- checked against the CPU
+    ORACLE run frame by frame (stale frame-0 neighbour lists, src/model_operations.py:8 on the frame's coordinates), not
+    against the model itself.  The 48-atom molecule has sink-padded neighbour slots, which read X[-1] of whatever is in
+    the batch: such molecules must be run one frame per forward to keep the reference's numbers."""
     import torch
+    from oracle import pesto_oracle as O
     from pesto_b200.data_encoding import extract_topology
     from pesto_b200.dataset import collate_batch_features
     from pesto_b200.md import predict_trajectory
     from pesto_b200.synth import synth_structure, one_hot_features, dense_membership
-    model = cuda_models("i_v4_0")
-    X, el, rid = synth_structure(700, 99)
+    model = cuda_models("i_v4_0", mode)
+    tol = 2e-4 if mode == "fp32" else 3e-4
+    X, el, rid = synth_structure(n_atoms, 99)
     g = torch.Generator().manual_seed(5)
     T = 7
     X_traj = X.unsqueeze(1) + 0.3 * torch.randn(X.shape[0], T, 3, generator=g)       # thermal motion around frame 0
@@ -86,36 +92,42 @@ def test_trajectory_mode_equals_frame_by_frame(cuda_models):
     q, M = one_hot_features(el), dense_membership(rid)
     ids0 = extract_topology(X_traj[:, 0].cuda(), 64)[0]
     _, ids1, qc, Mc = collate_batch_features([[X_traj[:, 0].cuda(), ids0, q.cuda(), M.cuda()]])
-    with torch.no_grad():
-        ref = torch.stack([model(X_traj[:, i].cuda(), ids1, qc, Mc.float()) for i in range(T)])
+    W = load_weights("i_v4_0")
+    n_res = int(rid.max()) + 1
+    ref = torch.stack([O.forward(W, X_traj[:, i].contiguous(), ids1.cpu(), q, rid, n_res) for i in range(T)])
     for per in (None, 3):
-        z = predict_trajectory(model, X_traj, ids1, q, M, frames_per_batch=per)
+        z = predict_trajectory(model, X_traj, ids1, q, M, frames_per_batch=per).cpu()
         assert z.shape == ref.shape
-        assert (z - ref).abs().max().item() <= 2e-5
-    z2 = predict_trajectory(model, X_traj.cuda(), ids1, q, rid, frames=[1, 5])
-    assert (z2 - ref[[1, 5]]).abs().max().item() <= 2e-5
+        assert (z - ref).abs().max().item() <= tol
+    z2 = predict_trajectory(model, X_traj.cuda(), ids1, q, rid, frames=[1, 5]).cpu()
+    assert (z2 - ref[[1, 5]]).abs().max().item() <= tol
 
 
-def test_structure_runner_equals_one_by_one(cuda_models):
-    """interfaceome/apply_model.py:49-82 pattern: packing structures into batches gives each structure the logits of its
-    own single forward; batches respect the atom budget; order is preserved."""
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_structure_runner_equals_one_by_one(cuda_models, mode):
+    """interfaceome/apply_model.py:49-82 pattern: packing structures into batches gives each structure the logits the CPU
+    ORACLE computes for it alone (the reference's one-structure-at-a-time loop); batches respect the atom budget; order
+    is preserved.  Structures with fewer than 64 atoms (sink-padded neighbour slots read X[-1] of the batch,
+    src/model_operations.py:8) get a batch of their own, so they too keep the reference's numbers."""
     import numpy as np
     import torch
-    from pesto_b200.data_encoding import extract_topology, std_elements
+    from oracle import pesto_oracle as O
+    from pesto_b200.data_encoding import std_elements
     from pesto_b200.runner import pack_batches, predict_structures
     from pesto_b200.synth import synth_structure, one_hot_features
-    model = cuda_models("i_v4_0")
+    model = cuda_models("i_v4_0", mode)
+    W = load_weights("i_v4_0")
+    sizes = [300, 70, 900, 40, 513, 64, 1200]
     structures, singles = [], []
-    for k, n in enumerate([300, 70, 900, 513, 64, 1200]):       # >= 64 atoms each: sink-padded slots read X[-1] of the BATCH (src/model_operations.py:8)
+    for k, n in enumerate(sizes):
         X, el, rid = synth_structure(n, 1000 + k)
         structures.append({"xyz": X.numpy(), "element": std_elements[el.numpy()], "resid": rid.numpy() * 3 + 7})
-        ids1 = extract_topology(X.cuda(), 64)[0] + 1
-        if ids1.shape[1] < 64:
-            ids1 = torch.nn.functional.pad(ids1, (0, 64 - ids1.shape[1]), value=0)
-        with torch.no_grad():
-            singles.append(model(X.cuda(), ids1, one_hot_features(el).cuda(), rid.int().cuda()).cpu())
-    assert pack_batches([300, 70, 900, 513, 64, 1200], 1300) == [[0, 1, 2], [3, 4], [5]]
+        q0 = one_hot_features(el)
+        n_res = int(rid.max()) + 1
+        ids1 = O.collate([(X, O.extract_topology(X, 64)[0], q0, rid, n_res)])[1]
+        singles.append(O.forward(W, X, ids1, q0, rid, n_res))
+    assert pack_batches(sizes, 1300) == [[0, 1, 2], [3], [4, 5], [6]]
     got = list(predict_structures(model, structures, target_atoms=1300))
-    assert [i for i, _ in got] == list(range(6))
+    assert [i for i, _ in got] == list(range(len(sizes)))
     for (i, z), ref in zip(got, singles):
-        assert z.shape == ref.shape and (z - ref).abs().max().item() <= 2e-5, i
+        assert z.shape == ref.shape and (z - ref).abs().max().item() <= (2e-4 if mode == "fp32" else 3e-4), i

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, load_case, load_weights, case_tensors
+from conftest import GOLDEN, BOTH_MODES, load_case, load_weights, case_tensors
 from oracle import pesto_oracle as O
 from oracle import scoring
 from pesto_b200.synth import synth_structure, one_hot_features, dense_membership, BASE_SEED
@@ -192,8 +192,10 @@ def test_per_layer_taps(cuda_models):
             assert float(q[0].abs().max()) == 0.0 and float(p[0].abs().max()) == 0.0     # sink row stays zero
 
 
-def test_benchmark_table_53_structures(cuda_models):
-    """BASELINE config 2: all 53 pdbs_test structures through extract_topology -> collate -> Model.forward.
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_benchmark_table_53_structures(cuda_models, mode):
+    """BASELINE config 2 (the workload bench.py times), in the FFMA mode and in the timed tensor-core mode: all 53
+    pdbs_test structures through extract_topology -> collate -> Model.forward.
 
     21 of the 132 417 rows contain an exact fp32 distance tie whose order torch.topk leaves unspecified; in one row
     (XL/4XL5, atom 1829) the tie straddles the nn=32 prefix, so the neighbour SET of that atom is ambiguous and the
@@ -204,7 +206,7 @@ def test_benchmark_table_53_structures(cuda_models):
     from pesto_b200.data_encoding import extract_topology
     from pesto_b200.dataset import collate_batch_features
     g = dict(np.load(os.path.join(GOLDEN, "pdbs_test_53.npz")))
-    model = cuda_models("i_v4_1")
+    model = cuda_models("i_v4_1", mode)
     aoff = np.concatenate([[0], np.cumsum(g["sizes"])])
     roff = np.concatenate([[0], np.cumsum(g["n_res"])])
     worst, worst_own, mismatched = 0.0, 0.0, []
@@ -236,24 +238,27 @@ def test_benchmark_table_53_structures(cuda_models):
     assert not mismatched, mismatched[:3]
 
 
-def test_synth8192_full_size(cuda_models):
-    """Full-size (N = 8192, k = 64, i_v4_1) against the reference's logits (75 s of CPU, stored)."""
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_synth8192_full_size(cuda_models, mode):
+    """Full-size (N = 8192, k = 64, i_v4_1: the north_star configuration) against the reference's logits (75 s of CPU, stored)."""
     from pesto_b200.data_encoding import extract_topology
     g = dict(np.load(os.path.join(GOLDEN, "case_synth8192.npz")))
     X, el, rid = synth_structure(8192, BASE_SEED)
     Xd = X.cuda()
     ids1 = extract_topology(Xd, 64)[0] + 1
-    z = cuda_models("i_v4_1")(Xd, ids1, one_hot_features(el).cuda(), rid.int().cuda(), n_res=1024).cpu()
+    z = cuda_models("i_v4_1", mode)(Xd, ids1, one_hot_features(el).cuda(), rid.int().cuda(), n_res=1024).cpu()
     err = (z - torch.from_numpy(g["z_i_v4_1"])).abs().max().item()
     assert err <= LOGIT_TOL, err
+    assert err <= (FP32_EXPECTED if mode == "fp32" else 3e-4), err
 
 
 # ------------------------------------------------------------------------------------------------- properties
-def test_batched_equals_separate(cuda_models):
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_batched_equals_separate(cuda_models, mode):
     """Structures are independent: a collated batch gives the same logits as separate forwards."""
     from pesto_b200.data_encoding import extract_topology
     from pesto_b200.dataset import collate_batch_features
-    model = cuda_models("i_v4_0")
+    model = cuda_models("i_v4_0", mode)
     parts, zs = [], []
     for k, n in enumerate((700, 1301, 96)):
         X, el, rid = synth_structure(n, 100 + k)
@@ -265,10 +270,11 @@ def test_batched_equals_separate(cuda_models):
     assert (zb - torch.cat(zs)).abs().max().item() <= 1e-4
 
 
-def test_rigid_motion_invariance_full_size(cuda_models):
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_rigid_motion_invariance_full_size(cuda_models, mode):
     """Logits are invariant to rotation + translation of the input cloud (N = 8192)."""
     from pesto_b200.data_encoding import extract_topology
-    model = cuda_models("i_v4_1")
+    model = cuda_models("i_v4_1", mode)
     X, el, rid = synth_structure(8192, 77)
     q0 = one_hot_features(el).cuda()
     ridd = rid.int().cuda()
@@ -283,10 +289,11 @@ def test_rigid_motion_invariance_full_size(cuda_models):
     assert (z0 - z1).abs().max().item() <= 2e-3
 
 
-def test_atom_permutation_equivariance(cuda_models):
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_atom_permutation_equivariance(cuda_models, mode):
     """Relabelling atoms (and their ids) leaves the per-residue logits unchanged."""
     from pesto_b200.data_encoding import extract_topology
-    model = cuda_models("i_v4_0")
+    model = cuda_models("i_v4_0", mode)
     X, el, rid = synth_structure(1500, 31)
     g = torch.Generator().manual_seed(2)
     perm = torch.randperm(1500, generator=g)
@@ -395,30 +402,35 @@ def test_logits_f16_speed_mode_reports_its_error(cuda_models):
 
 
 def test_config4_large_chain_32768(cuda_models):
-    """BASELINE config 4 (one N = 32 768 chain, i_v4_1): too large for the CPU oracle in test time, so checked through
-    size-independent properties: finite logits, rigid-motion invariance, and agreement with the fp32 (FFMA) path."""
+    """BASELINE config 4 (one N = 32 768 chain, i_v4_1) in the timed tensor-core mode: too large for the CPU oracle in
+    test time, so checked through size-independent properties: finite logits, rigid-motion invariance, and agreement of
+    the tcgen05 path (f16x3) with the FFMA path (fp32), which the golden cases pin to the reference."""
     from pesto_b200.data_encoding import extract_topology
     X, el, rid = synth_structure(32768, BASE_SEED + 4)
     Xd, q0, ridd = X.cuda(), one_hot_features(el).cuda(), rid.int().cuda()
     ids0 = extract_topology(Xd, 64)[0]
     assert ids0.shape == (32768, 64) and int(ids0.min()) >= 0 and int(ids0.max()) < 32768
     ids1 = ids0 + 1
-    model = cuda_models("i_v4_1")
+    model = cuda_models("i_v4_1", "f16x3")
+    assert model.mode == "f16x3"
     z = model(Xd, ids1, q0, ridd, n_res=4096)
     assert z.shape == (4096, 5) and torch.isfinite(z).all()
     g = torch.Generator().manual_seed(4)
     Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
     X2 = (X.double() @ Q + torch.tensor([-3.0, 100.0, 55.5], dtype=torch.float64)).float().cuda()
     assert (z - model(X2, ids1, q0, ridd, n_res=4096)).abs().max().item() <= 2e-3
-    z32 = model(Xd, ids1, q0, ridd, n_res=4096, mode="fp32")
-    assert (z - z32).abs().max().item() <= LOGIT_TOL
+    z32 = cuda_models("i_v4_1", "fp32")(Xd, ids1, q0, ridd, n_res=4096)
+    d = (z - z32).abs().max().item()
+    assert 0.0 < d <= LOGIT_TOL, d          # two different arithmetic paths (d == 0 would mean the same kernel ran twice)
 
 
-def test_config3_batch_of_8192_atom_structures(cuda_models):
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_config3_batch_of_8192_atom_structures(cuda_models, mode):
     """BASELINE config 3 (i_v4_0, synthetic N = 8192 structures collated into one batch): the batched forward over
-    several structures equals the separate forwards (the full 32-structure batch is timed by profiles/bench_configs.py)."""
+    several structures equals the separate forwards, and the first structure matches the CPU oracle
+    (the full 32-structure batch is timed by profiles/bench_configs.py)."""
     from pesto_b200.data_encoding import batch_topology, extract_topology
-    model = cuda_models("i_v4_0")
+    model = cuda_models("i_v4_0", mode)
     n, n_struct = 8192, 4
     Xs, els, rids = zip(*[synth_structure(n, BASE_SEED + 100 + s) for s in range(n_struct)])
     Xb = torch.cat(Xs).cuda()
@@ -432,3 +444,6 @@ def test_config3_batch_of_8192_atom_structures(cuda_models):
         assert torch.equal(ids1b[s * n:(s + 1) * n] - s * n, ids1)          # 1-based global ids of collate_batch_features
         zs = model(Xd, ids1, one_hot_features(els[s]).cuda(), rids[s].int().cuda(), n_res=n // 8)
         assert (zb[s * (n // 8):(s + 1) * (n // 8)] - zs).abs().max().item() <= 1e-4
+        if s == 0:          # 16 layers x 8192 atoms: ~20 s of CPU oracle
+            zo = O.forward(load_weights("i_v4_0"), Xs[0], ids1.cpu(), one_hot_features(els[0]), rids[0], n // 8)
+            assert (zs.cpu() - zo).abs().max().item() <= (FP32_EXPECTED if mode == "fp32" else 3e-4)
