@@ -155,15 +155,22 @@ int pesto_debug_umma_probe(const float *A, const float *B, float *D, int K, int 
  * int64) for the first max_tiles tiles of each half; buf == NULL switches it off. */
 int pesto_debug_edge_timeline(void *buf, int max_tiles);
 
+/* Debug: cycles of a chain of n_mma tcgen05.mma (M = 128, K = 16, fp16 operands, zeros) with the given shared-memory operand
+ * layouts (descriptor layout type 0 none / 2 SWIZZLE_128B / 4 SWIZZLE_64B / 6 SWIZZLE_32B, byte strides, bytes per K step;
+ * *_major_mn != 0: MN-major operand) or with the A operand in TMEM; out (device int64[2]) = issue cycles, cycles until complete. */
+int pesto_debug_mma_time(int n_mma, int N, int a_major_mn, int a_layout, int a_lbo, int a_sbo, int a_kstep, int b_major_mn,
+                         int b_layout, int b_lbo, int b_sbo, int b_kstep, int a_tmem, long long *out, void *stream);
+
 /* Debug: building blocks of the edge kernel's tensor-core reduction in isolation (csrc/rmma_probe.cu).  Gathers the
  * 128 rows ids[] of p16 (device, fp16 [n_rows][192] = hi plane 96 | lo plane 96) with TMA tile::gather4 into
  * shared memory and computes D[m][n] = sum_k (hi + lo)(ids[k], m) * W[n][k] (W: device fp32 [16][128]) as a 3-term
  * split tcgen05.mma with both operands MN-major in shared memory -> D device fp32 [128][16] (rows >= 96 unspecified);
  * Prec (device fp32 [128][96]) receives hi + lo of every gathered row as read back by threads from the swizzled tile,
  * raw (optional, 48 KB) the tile's bytes.  a_/b_ lbo/sbo < 0 and idesc == 0 select the library's own descriptor values;
- * *status (device int) receives a stage id if a wait timed out. */
+ * issue_lanes: 1 = one lane issues the 192 gathers, 32 = the lanes of one warp issue six each.  status (device int[3]):
+ * [0] a stage id if a wait timed out, [1] clock cycles spent issuing, [2] cycles from the first issue until all rows landed. */
 int pesto_debug_rmma_probe(const void *p16, int n_rows, const int32_t *ids, const float *W, float *D, float *Prec, void *raw,
-                           int a_lbo, int a_sbo, int b_lbo, int b_sbo, int idesc, int *status, void *stream);
+                           int a_lbo, int a_sbo, int b_lbo, int b_sbo, int idesc, int issue_lanes, int *status, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side PDB text parser (no device work; every pointer is a HOST pointer).  Replaces the gemmi call inside

@@ -44,7 +44,8 @@ SIGNATURES = {
     "pesto_pdb_parse_host": (_i, [_c.c_char_p, _sz, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pesto_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pesto_debug_edge_timeline": (_i, [_vp, _i]),
-    "pesto_debug_rmma_probe": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pesto_debug_mma_time": (_i, [_i] * 13 + [_vp, _vp]),
+    "pesto_debug_rmma_probe": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -6,7 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +28,25 @@ int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return PESTO_OK;
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return PESTO_ECUDA;
+}
+
+int device_setup(const void *kernel, int dyn_smem, int *n_sm_out) {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel, and so is the SM count the
+    // persistent grids are sized with: both are cached per (kernel, device), not per process
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;       // -> SM count
+    int dev = 0;
+    PESTO_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({kernel, dev});
+    if (it == done.end()) {
+        if (dyn_smem > 0) PESTO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        int n_sm = 0;
+        PESTO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        it = done.emplace(std::make_pair(kernel, dev), n_sm).first;
+    }
+    *n_sm_out = it->second;
+    return PESTO_OK;
 }
 
 }  // namespace pesto
@@ -188,7 +209,7 @@ Workspace carve_workspace(void *base, int n_atoms, int n_res) {
     w.state_b = (float *)take(rows * SR * sizeof(float));
     w.ids32 = (int32_t *)take((size_t)n_atoms * KMAX * sizeof(int32_t));
     w.geom = (float *)take((size_t)n_atoms * KMAX * 4 * sizeof(float));
-    w.node = (float *)take(rows * (NODE_T_STRIDE + NODE_C_STRIDE + 256) * sizeof(float));
+    w.node = (float *)take(node_scratch_floats(n_atoms) * sizeof(float));
     w.rid = (int32_t *)take((size_t)n_atoms * sizeof(int32_t));
     w.status = (int32_t *)take(4 * sizeof(int32_t));
     w.pool = take(pool_scratch_bytes(n_atoms, n_res));
@@ -309,8 +330,8 @@ int pesto_prologue(const pesto_model_t *m, const float *X, const int64_t *ids1, 
                            (cudaStream_t)stream);
 }
 
-size_t pesto_node_scratch_bytes(int n_atoms) {   // per-atom factors T | C and the attention sums Z of one layer
-    return ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE + 256) * sizeof(float);
+size_t pesto_node_scratch_bytes(int n_atoms) {   // per-atom factors T | C, the attention sums Z and the fp16 p planes of one layer
+    return node_scratch_floats(n_atoms) * sizeof(float);
 }
 
 static int state_update_impl(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
@@ -327,8 +348,7 @@ static int state_update_impl(const pesto_model_t *m, int layer, int n_atoms, con
                                         (float *)node_scratch, (cudaStream_t)stream, ev);
     if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16)
         return launch_state_update_tc(m->layer(layer), m->layer_tc(layer), m->nn[layer], n_atoms, ids32, geom, state_in,
-                                      state_out, (float *)node_scratch,
-                                      (float *)node_scratch + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE), mode,
+                                      state_out, (float *)node_scratch, node_Z((float *)node_scratch, n_atoms), mode,
                                       (cudaStream_t)stream, ev);
     set_error("pesto_state_update: unknown mode %d", mode);
     return PESTO_EINVAL;
@@ -426,7 +446,7 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
         }
     } else if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16) {
         // tensor-core path: the per-atom tail of layer l and the per-atom head of layer l+1 share one launch
-        float *Z = w.node + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE);
+        float *Z = node_Z(w.node, n_atoms);
         // per-atom kernels: tcgen05 (default) or, with PESTO_NODE=ffma, the FP32-pipe version (A/B checks)
         static const bool node_ffma = getenv("PESTO_NODE") && !strcmp(getenv("PESTO_NODE"), "ffma");
         auto node_img = [&](int l) { return (const void *)((const unsigned char *)m->layer_tc(l) + tc_edge_bytes()); };

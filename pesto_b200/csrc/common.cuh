@@ -100,6 +100,12 @@ struct HeadLayout {
 constexpr int NODE_T_STRIDE = 128;                    // T_j, gathered per edge (row 0 = sink = 0)
 constexpr int NODE_C_STRIDE = 528;                    // U(128) | A_x(128) | A_y(128) | A_z(128) | Q(12)+pad(4)
 constexpr int NODE_C_Q = 512;
+constexpr int NODE_Z_STRIDE = 256;                    // attention sums of the edge kernel: Zq(2x32) | Zp(3x2x32)
+// node scratch of one layer: T | C | Z, each with n_atoms + 1 rows (row 0 = sink)
+__host__ __device__ inline size_t node_scratch_floats(int n_atoms) {
+    return ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE + NODE_Z_STRIDE);
+}
+inline float *node_Z(float *node_scratch, int n_atoms) { return node_scratch + ((size_t)n_atoms + 1) * (NODE_T_STRIDE + NODE_C_STRIDE); }
 
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (expf(x) - 1.0f); }
 
@@ -110,6 +116,9 @@ __device__ __forceinline__ float dist_exact(float dx, float dy, float dz) {
 
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
+// Per-device launch setup of a kernel: opt in to `dyn_smem` bytes of dynamic shared memory (a per-device function
+// attribute) the first time the kernel is launched on the current device, and return that device's SM count.
+int device_setup(const void *kernel, int dyn_smem, int *n_sm_out);
 
 #define PESTO_CUDA(call)                                             \
     do {                                                             \

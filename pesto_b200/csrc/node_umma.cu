@@ -529,14 +529,8 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
 template <bool SPLIT, bool FUSE_PREV, bool NEXT>
 int launch_node_umma_variant(const void *img_tail, const void *img_head, const float *state_prev, const float *Z,
                              float *state_new, int n_rows, float *nodeT, float *nodeC, cudaStream_t st) {
-    static int configured = 0, n_sm = 0;
-    if (!configured) {
-        PESTO_CUDA(cudaFuncSetAttribute(node_umma_kernel<SPLIT, FUSE_PREV, NEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NSM_TOTAL));
-        int dev = 0;
-        PESTO_CUDA(cudaGetDevice(&dev));
-        PESTO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        configured = 1;
-    }
+    int n_sm = 0;
+    { const int rc_ = device_setup((const void *)node_umma_kernel<SPLIT, FUSE_PREV, NEXT>, NSM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     const int n_tiles = (n_rows + 127) / 128;
     const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
     node_umma_kernel<SPLIT, FUSE_PREV, NEXT><<<grid, NODE_THREADS, NSM_TOTAL, st>>>(

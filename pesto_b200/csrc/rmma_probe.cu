@@ -36,7 +36,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_by
 __global__ void __launch_bounds__(128)
 rmma_probe_kernel(const __grid_constant__ CUtensorMap map, const int32_t *__restrict__ ids, const float *__restrict__ W,
                   float *__restrict__ D, float *__restrict__ Prec, uint32_t *__restrict__ raw, int a_lbo, int a_sbo, int b_lbo,
-                  int b_sbo, uint32_t idesc, int *status) {
+                  int b_sbo, uint32_t idesc, int issue_lanes, int *status) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bars[2];
@@ -67,17 +67,33 @@ rmma_probe_kernel(const __grid_constant__ CUtensorMap map, const int32_t *__rest
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tmem_base_s;
-    if (tid == 0) {
-        tc::mbar_arrive_expect_tx(&bars[0], PR_EDGES * 384);
-        for (int e4 = 0; e4 < PR_EDGES / 4; ++e4) {
-            const int r0 = ids[4 * e4], r1 = ids[4 * e4 + 1], r2 = ids[4 * e4 + 2], r3 = ids[4 * e4 + 3];
-#pragma unroll
-            for (int g = 0; g < 6; ++g)
-                tma_gather4(tc::smem_u32(smem + g * PR_GROUP + e4 * 256), &map, (g / 3) * 96 + (g % 3) * 32, r0, r1, r2, r3,
-                            tc::smem_u32(&bars[0]));
+    // timing of the gather (clock64 stamps -> status[1..2]): the 192 gather4 instructions of the tile are dealt round-robin
+    // to issue_lanes issuing threads: 1 = thread 0; 4 = lane 0 of every warp; 32 = the lanes of warp 0; 128 = every thread
+    __shared__ __align__(16) int ids_s[PR_EDGES];
+    ids_s[tid] = ids[tid];
+    long long t0 = 0, t1 = 0;
+    if (tid == 0) tc::mbar_arrive_expect_tx(&bars[0], PR_EDGES * 384);
+    __syncthreads();
+    const int lane_ = tid & 31;
+    const int issuer = issue_lanes == 1 ? (tid == 0 ? 0 : -1) : issue_lanes == 4 ? (lane_ == 0 ? warp : -1)
+                       : issue_lanes == 32 ? (warp == 0 ? lane_ : -1) : tid;
+    if (issuer >= 0) {
+        t0 = clock64();
+        const uint32_t bar_a = tc::smem_u32(&bars[0]), dst0 = tc::smem_u32(smem);
+#pragma unroll 2
+        for (int q = issuer; q < 6 * PR_EDGES / 4; q += issue_lanes) {
+            const int e4 = q / 6, g = q % 6;
+            const int4 r = *reinterpret_cast<const int4 *>(ids_s + 4 * e4);
+            tma_gather4(dst0 + g * PR_GROUP + e4 * 256, &map, (g / 3) * 96 + (g % 3) * 32, r.x, r.y, r.z, r.w, bar_a);
         }
+        t1 = clock64();
     }
     bool ok = tc::mbar_wait(&bars[0], 0, status, 1, 1u << 14);
+    if (tid == 0) {
+        const long long t2 = clock64();
+        status[1] = (int)(t1 - t0);
+        status[2] = (int)(t2 - t0);
+    }
     if (tid == 0 && ok) {
         tc::fence_after_sync();
         const uint32_t p = tc::smem_u32(smem), b = tc::smem_u32(smem + PR_B);
@@ -166,7 +182,7 @@ int make_row_gather_map(void *map_out, const void *base, int n_rows, int row_ele
 }  // namespace pesto
 
 extern "C" int pesto_debug_rmma_probe(const void *p16, int n_rows, const int32_t *ids, const float *W, float *D, float *Prec,
-                                      void *raw, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int idesc, int *status, void *stream) {
+                                      void *raw, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int idesc, int issue_lanes, int *status, void *stream) {
     using namespace pesto;
     CUtensorMap map;
     int rc = make_row_gather_map(&map, p16, n_rows, 192, 384, 32, 2);
@@ -175,7 +191,76 @@ extern "C" int pesto_debug_rmma_probe(const void *p16, int n_rows, const int32_t
     PESTO_CUDA(cudaFuncSetAttribute(rmma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));
     rmma_probe_kernel<<<1, 128, PR_SMEM, (cudaStream_t)stream>>>(map, ids, W, D, Prec, (uint32_t *)raw, a_lbo >= 0 ? a_lbo : PR_GROUP,
                                                                a_sbo >= 0 ? a_sbo : 512, b_lbo >= 0 ? b_lbo : 128,
-                                                               b_sbo >= 0 ? b_sbo : 2048, id, status);
+                                                               b_sbo >= 0 ? b_sbo : 2048, id, issue_lanes, status);
+    PESTO_CUDA(cudaGetLastError());
+    return PESTO_OK;
+}
+
+// ---- timing of smem-operand MMA chains (which operand layouts the tensor core reads at full speed) -----------------------
+namespace pesto {
+namespace {
+__global__ void __launch_bounds__(128)
+mma_time_kernel(int n_mma, int N, uint32_t a_layout, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_layout, uint32_t b_lbo,
+                uint32_t b_sbo, uint32_t b_kstep, uint32_t idesc, int a_tmem, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_mbar_init();
+    }
+    for (int u = tid; u < 96 * 1024 / 4; u += 128) reinterpret_cast<uint32_t *>(smem)[u] = 0u;
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    if (warp_u == 0) {
+        // warp-uniform operands (kernel parameters and the broadcast TMEM base): the issue loop runs on the uniform datapath,
+        // eight K steps unrolled with descriptors that differ by constants
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0), a0 = tc::smem_u32(smem), b0 = tc::smem_u32(smem + 64 * 1024);
+        const uint64_t ad0 = tc::smem_desc(a0, a_lbo, a_sbo) | ((uint64_t)a_layout << 61);
+        const uint64_t bd0 = tc::smem_desc(b0, b_lbo, b_sbo) | ((uint64_t)b_layout << 61);
+        const uint64_t astep = a_kstep >> 4, bstep = b_kstep >> 4;
+        long long t0 = 0, t1 = 0;
+        if (tc::elect_one()) {
+            t0 = clock64();
+            for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (a_tmem) tc::umma_ts(tb + 128, tb + 8 * ks, bd0 + ks * bstep, idesc, (i | ks) > 0);
+                    else tc::umma_ss(tb + 128, ad0 + ks * astep, bd0 + ks * bstep, idesc, (i | ks) > 0);
+                }
+            }
+            t1 = clock64();
+            tc::umma_commit(&bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(&bar, 0, nullptr, 0, 1u << 16);
+        const long long t2 = clock64();
+        if (t0) {
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 256);
+}
+}  // namespace
+}  // namespace pesto
+
+/* Debug: cycles of a chain of n_mma tcgen05.mma (M = 128, K = 16, fp16) with the given operand descriptors (layout type as in
+ * the descriptor's bits [61,64); a_tmem != 0: A operand from TMEM); out (device int64[2]) = issue cycles, cycles until done. */
+extern "C" int pesto_debug_mma_time(int n_mma, int N, int a_major_mn, int a_layout, int a_lbo, int a_sbo, int a_kstep, int b_major_mn,
+                                    int b_layout, int b_lbo, int b_sbo, int b_kstep, int a_tmem, long long *out, void *stream) {
+    using namespace pesto;
+    const uint32_t id = tc::idesc_h16(128, N) | ((uint32_t)(a_major_mn != 0) << 15) | ((uint32_t)(b_major_mn != 0) << 16);
+    PESTO_CUDA(cudaFuncSetAttribute(mma_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    mma_time_kernel<<<1, 128, 96 * 1024, (cudaStream_t)stream>>>(n_mma, N, a_layout, a_lbo, a_sbo, a_kstep, b_layout, b_lbo, b_sbo,
+                                                               b_kstep, id, a_tmem, out);
     PESTO_CUDA(cudaGetLastError());
     return PESTO_OK;
 }

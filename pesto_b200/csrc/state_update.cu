@@ -414,14 +414,8 @@ edge_kernel_fp32(const float *__restrict__ lw, int n_atoms, const int32_t *__res
 template <int NN>
 int launch_edge(const float *lw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
                 const float *nodeT, const float *nodeC, float *state_out, cudaStream_t st) {
-    static int configured = 0, n_sm = 0;
-    if (!configured) {
-        PESTO_CUDA(cudaFuncSetAttribute(edge_kernel_fp32<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SMEM));
-        int dev = 0;
-        PESTO_CUDA(cudaGetDevice(&dev));
-        PESTO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        configured = 1;
-    }
+    int n_sm = 0;
+    { const int rc_ = device_setup((const void *)edge_kernel_fp32<NN>, (int)EDGE_SMEM, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     constexpr int TA = EDGE_THREADS / NN;
     int n_tiles = (n_atoms + TA - 1) / TA;
     int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;

@@ -69,7 +69,8 @@ def test_edge_timeline_debug_entry():
     assert int(buf.abs().sum()) == 0
 
 
-def test_rmma_probe_gather4_and_mn_major_operands():
+@pytest.mark.parametrize("issue_lanes", [1, 4, 32, 128])
+def test_rmma_probe_gather4_and_mn_major_operands(issue_lanes):
     """TMA tile::gather4 (64-byte swizzle) of fp16 hi|lo neighbour records + tcgen05.mma with both operands MN-major
     in shared memory (A = the records as they landed, B = per-edge weights written by threads): the building blocks
     of the edge kernel's tensor-core reduction, against a float64 matmul."""
@@ -90,16 +91,17 @@ def test_rmma_probe_gather4_and_mn_major_operands():
     D = torch.full((128, 16), float("nan"), device="cuda")
     Prec = torch.full((128, 96), float("nan"), device="cuda")
     raw = torch.zeros(48 * 1024 // 4, dtype=torch.int32, device="cuda")
-    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    status = torch.zeros(3, dtype=torch.int32, device="cuda")
     ids_d, W_d = ids.cuda(), W.cuda()                                  # (named: the pointers must outlive the call)
     _lib.check(lib.pesto_debug_rmma_probe(p16.data_ptr(), n_rows, ids_d.data_ptr(), W_d.data_ptr(), D.data_ptr(),
-                                          Prec.data_ptr(), raw.data_ptr(), -1, -1, -1, -1, 0, status.data_ptr(), None), "rmma probe")
+                                          Prec.data_ptr(), raw.data_ptr(), -1, -1, -1, -1, 0, issue_lanes, status.data_ptr(), None), "rmma probe")
     torch.cuda.synchronize()
+    print(f"gather of 128 x 384 B rows, {issue_lanes} issuing lane(s): issue {int(status[1])} cycles, landed after {int(status[2])} cycles")
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         np.savez(os.path.join(out, "rmma_probe.npz"), D=D.cpu().numpy(), Prec=Prec.cpu().numpy(), raw=raw.cpu().numpy(),
                  p16=p16.cpu().numpy().view(np.uint16), ids=ids.numpy(), W=W.numpy(), status=status.cpu().numpy())
-    assert int(status.item()) == 0, f"probe wait timed out at stage {int(status.item())}"
+    assert int(status[0]) == 0, f"probe wait timed out at stage {int(status[0])}"
     pg = (hi.double() + lo.double())[ids.long()]                       # [128 edges][96]
     assert (Prec.cpu().double() - pg).abs().max().item() < 1e-6        # thread-side read of the swizzled tile
     ref = pg.T @ W.double().T                                          # [96][16]
