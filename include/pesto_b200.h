@@ -30,6 +30,8 @@ extern "C" {
 #define PESTO_EINVAL       -1   /* bad argument (shape, null pointer, unsupported size) */
 #define PESTO_ECUDA        -2   /* a CUDA runtime call / kernel launch failed            */
 #define PESTO_ESTATE       -3   /* model not finalized, missing tensor, ...              */
+#define PESTO_EINPUT       -4   /* input data the device found invalid (pesto_forward_status) */
+#define PESTO_STATUS_WORDS  8   /* int32 status words of a forward's workspace              */
 
 #define PESTO_NS           32   /* state width Ns            (model/config.py: 'Ns': 32) */
 #define PESTO_NH            2   /* attention heads Nh                                    */
@@ -143,6 +145,19 @@ size_t pesto_forward_workspace_bytes(int n_atoms, int n_res);
 int    pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, int ids_cols,
                      const float *q0, const float *M, const int32_t *rid, int n_atoms, int n_res,
                      float *z, void *workspace, size_t workspace_bytes, int mode, void *stream);
+
+/* Errors only the device can detect never abort and never force a synchronisation: they set a status word in the
+ * workspace and make every logit NaN.  pesto_forward_status copies the PESTO_STATUS_WORDS words of the forward that
+ * last used `workspace` (same n_atoms, n_res) to status_host, synchronising `stream`, and returns PESTO_EINPUT
+ * ([1] a neighbour id out of range, [2] a row of M not one-hot, [4] a residue index out of range) or PESTO_ECUDA
+ * ([3] = id of a tensor-core stage whose completion never arrived: the kernels' bounded waits gave up) with
+ * pesto_last_error() set; PESTO_OK if the forward was clean.  Callers that synchronise anyway (to read z) call it there. */
+int pesto_forward_status(const void *workspace, int n_atoms, int n_res, int32_t *status_host, void *stream);
+
+/* Debug: simulate a hung tensor-core stage (on != 0: the edge kernels never signal their third-layer GEMMs and wait only
+ * briefly); pesto_debug_watchdog reads and clears the device word that staged calls (pesto_state_update) report into. */
+int pesto_debug_force_watchdog(int on);
+int pesto_debug_watchdog(int32_t *value_host);
 
 /* Debug / self-test: D[128,N] = A[128,K] * B[N,K]^T on the tensor cores with exactly the operand staging of the
  * fused kernel (A thread-per-row in TMEM, B K-major un-swizzled in shared memory); split != 0 selects the 3-term

@@ -40,6 +40,9 @@ SIGNATURES = {
     "pesto_forward_workspace_bytes": (_sz, [_i, _i]),
     "pesto_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pesto_forward_launch_count": (_i, [_vp, _i, _i]),
+    "pesto_forward_status": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pesto_debug_force_watchdog": (_i, [_i]),
+    "pesto_debug_watchdog": (_i, [_vp]),
     "pesto_pdb_count_atoms_host": (_i, [_c.c_char_p, _sz]),
     "pesto_pdb_parse_host": (_i, [_c.c_char_p, _sz, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pesto_debug_umma_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

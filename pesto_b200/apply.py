@@ -41,7 +41,9 @@ def predict_structure(model, structure, device="cuda"):
         ids_topk = extract_topology(X, 64)[0]
         X, ids_topk, q, M = collate_batch_features([[X, ids_topk, q.to(device), M.to(device)]])
         z = model(X, ids_topk, q, M.float())
-        return torch.sigmoid(z).cpu().numpy()
+        p = torch.sigmoid(z).cpu().numpy()
+        model.raise_if_failed(X.device)        # (the copy above synchronised: device-side input / watchdog flags -> PestoError)
+        return p
 
 
 def apply_to_pdb(model, pdb_filepath, device="cuda", out_prefix=None):

@@ -49,6 +49,21 @@ int device_setup(const void *kernel, int dyn_smem, int *n_sm_out) {
     return PESTO_OK;
 }
 
+int *device_watchdog_word() {
+    static std::mutex mu;
+    static std::map<int, int *> words;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = words.find(dev);
+    if (it == words.end()) {
+        int *p = nullptr;
+        if (cudaMalloc((void **)&p, sizeof(int)) != cudaSuccess || cudaMemset(p, 0, sizeof(int)) != cudaSuccess) return nullptr;
+        it = words.emplace(dev, p).first;
+    }
+    return it->second;
+}
+
 }  // namespace pesto
 
 using namespace pesto;
@@ -211,7 +226,7 @@ Workspace carve_workspace(void *base, int n_atoms, int n_res) {
     w.geom = (float *)take((size_t)n_atoms * KMAX * 4 * sizeof(float));
     w.node = (float *)take(node_scratch_floats(n_atoms) * sizeof(float));
     w.rid = (int32_t *)take((size_t)n_atoms * sizeof(int32_t));
-    w.status = (int32_t *)take(4 * sizeof(int32_t));
+    w.status = (int32_t *)take(PESTO_STATUS_WORDS * sizeof(int32_t));
     w.pool = take(pool_scratch_bytes(n_atoms, n_res));
     w.total = o;
     return w;
@@ -435,6 +450,8 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
         return PESTO_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    PESTO_CUDA(cudaMemsetAsync(w.status, 0, PESTO_STATUS_WORDS * sizeof(int32_t), st));
+    int *wd = w.status + 3;      // a tensor-core stage that never completes records its id here -> NaN logits, pesto_forward_status
     int rc = launch_prologue(m->head(), m->q0_dim, X, ids1, ids_cols, q0, n_atoms, w.state_a, w.ids32, w.geom, w.status, st);
     if (rc != PESTO_OK) return rc;
     float *cur = w.state_a, *nxt = w.state_b;
@@ -447,18 +464,14 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
     } else if (mode == PESTO_MODE_BF16X3 || mode == PESTO_MODE_BF16) {
         // tensor-core path: the per-atom tail of layer l and the per-atom head of layer l+1 share one launch
         float *Z = node_Z(w.node, n_atoms);
-        // per-atom kernels: tcgen05 (default) or, with PESTO_NODE=ffma, the FP32-pipe version (A/B checks)
-        static const bool node_ffma = getenv("PESTO_NODE") && !strcmp(getenv("PESTO_NODE"), "ffma");
         auto node_img = [&](int l) { return (const void *)((const unsigned char *)m->layer_tc(l) + tc_edge_bytes()); };
-        rc = node_ffma ? launch_node_fused(nullptr, m->layer(0), cur, nullptr, nullptr, n_atoms, w.node, st)
-                       : launch_node_umma(nullptr, node_img(0), cur, nullptr, nullptr, n_atoms, w.node, mode, st);
+        rc = launch_node_umma(nullptr, node_img(0), cur, nullptr, nullptr, n_atoms, w.node, mode, st, wd);
         if (rc != PESTO_OK) return rc;
         for (int l = 0; l < m->n_layers; ++l) {
-            rc = launch_edge_tc_layer(m->layer(l), m->layer_tc(l), m->nn[l], n_atoms, w.ids32, w.geom, cur, w.node, Z, mode, st);
+            rc = launch_edge_tc_layer(m->layer(l), m->layer_tc(l), m->nn[l], n_atoms, w.ids32, w.geom, cur, w.node, Z, mode, st, wd);
             if (rc != PESTO_OK) return rc;
             const bool more = l + 1 < m->n_layers;
-            rc = node_ffma ? launch_node_fused(m->layer(l), more ? m->layer(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, st)
-                           : launch_node_umma(node_img(l), more ? node_img(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, mode, st);
+            rc = launch_node_umma(node_img(l), more ? node_img(l + 1) : nullptr, cur, Z, nxt, n_atoms, w.node, mode, st, wd);
             if (rc != PESTO_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
         }
@@ -471,11 +484,41 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
         rc = launch_residue_index(M, n_atoms, n_res, w.rid, w.status + 2, st);
         if (rc != PESTO_OK) return rc;
         rid_dev = w.rid;
-    } else {
-        PESTO_CUDA(cudaMemsetAsync(w.status + 2, 0, sizeof(int32_t), st));
     }
-    // status[1] = id out of range, status[2] = membership not one-hot: both poison z with NaN
+    // status[1] = id out of range, [2] = membership not one-hot, [3] = a tensor-core stage timed out: each poisons z with NaN
+    // ([4] = residue index out of range, set by the pool kernels)
     return launch_pool_decode(m->head(), cur, rid_dev, n_atoms, n_res, z, w.pool, w.status + 1, st);
+}
+
+int pesto_forward_status(const void *workspace, int n_atoms, int n_res, int32_t *status_host, void *stream) {
+    if (!workspace || !status_host || n_atoms < 1 || n_res < 1) {
+        set_error("pesto_forward_status: null pointer or bad sizes");
+        return PESTO_EINVAL;
+    }
+    Workspace w = carve_workspace(const_cast<void *>(workspace), n_atoms, n_res);
+    cudaStream_t st = (cudaStream_t)stream;
+    PESTO_CUDA(cudaMemcpyAsync(status_host, w.status, PESTO_STATUS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PESTO_CUDA(cudaStreamSynchronize(st));
+    status_host[0] = 0;                                    // (word 0 is geometry scratch, not a flag)
+    if (status_host[1]) { set_error("pesto_forward: a neighbour id in ids_topk is out of range [0, n_atoms]"); return PESTO_EINPUT; }
+    if (status_host[2]) { set_error("pesto_forward: a row of the membership matrix M is not one-hot"); return PESTO_EINPUT; }
+    if (status_host[4]) { set_error("pesto_forward: a residue index is out of range [0, n_res)"); return PESTO_EINPUT; }
+    if (status_host[3]) {
+        set_error("pesto_forward: tensor-core stage %d never completed (watchdog): the logits are NaN", status_host[3]);
+        return PESTO_ECUDA;
+    }
+    return PESTO_OK;
+}
+
+int pesto_debug_watchdog(int32_t *value_host) {
+    int *p = device_watchdog_word();
+    if (!p || !value_host) {
+        set_error("pesto_debug_watchdog: no device word");
+        return PESTO_ECUDA;
+    }
+    PESTO_CUDA(cudaMemcpy(value_host, p, sizeof(int), cudaMemcpyDeviceToHost));
+    PESTO_CUDA(cudaMemset(p, 0, sizeof(int)));
+    return PESTO_OK;
 }
 
 int pesto_forward_launch_count(const pesto_model_t *m, int dense_m, int mode) {

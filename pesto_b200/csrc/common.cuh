@@ -119,6 +119,9 @@ int check_cuda(cudaError_t e, const char *what);
 // Per-device launch setup of a kernel: opt in to `dyn_smem` bytes of dynamic shared memory (a per-device function
 // attribute) the first time the kernel is launched on the current device, and return that device's SM count.
 int device_setup(const void *kernel, int dyn_smem, int *n_sm_out);
+// Device word (one per device, allocated on first use) that receives the stage id of a tensor-core wait that timed out
+// when a launch is not given a status word of its own (staged API); nullptr if it cannot be allocated.
+int *device_watchdog_word();
 
 #define PESTO_CUDA(call)                                             \
     do {                                                             \
@@ -139,12 +142,12 @@ int launch_node(const float *layer_w, int n_atoms, const float *state_in, float 
 int launch_node_fused(const float *lw_prev, const float *lw_next, const float *state_prev, const float *Z,
                       float *state_new, int n_atoms, float *node_scratch, cudaStream_t st);
 int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
-                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st);
+                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st, int *wd = nullptr);
 int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
                            const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
-                           cudaStream_t st, cudaEvent_t *ev);
+                           cudaStream_t st, cudaEvent_t *ev, int *wd = nullptr);
 int launch_node_umma(const void *img_tail, const void *img_head, const float *state_prev, const float *Z, float *state_new,
-                     int n_atoms, float *node_scratch, int mode, cudaStream_t st);
+                     int n_atoms, float *node_scratch, int mode, cudaStream_t st, int *wd = nullptr);
 size_t node_tc_layer_bytes();
 void pack_node_tc_layer(const float *layer_blob_host, void *dst_host);
 size_t tc_edge_bytes();          // the per-layer image block is [edge images | node images]
@@ -152,7 +155,7 @@ size_t tc_layer_bytes();
 void pack_tc_layer(const float *layer_blob_host, void *dst_host);
 int launch_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, cudaStream_t st);
 int launch_pool_decode(const float *head_w, const float *state, const int32_t *rid, int n_atoms, int n_res,
-                       float *z, void *scratch, const int32_t *poison, cudaStream_t st);
+                       float *z, void *scratch, int32_t *poison, cudaStream_t st);      // poison: status words 1..4 of the forward (or nullptr)
 int launch_unpack_state(const float *state, int n_atoms, float *q, float *p, cudaStream_t st);
 size_t pool_scratch_bytes(int n_atoms, int n_res);
 size_t knn_scratch_bytes(int n_atoms, int n_seg);

@@ -179,13 +179,12 @@ __device__ __forceinline__ void node_gemm(uint32_t tbase, uint32_t d_col, uint32
     }
 }
 
-__device__ int g_node_watchdog = 0;
 
 template <bool SPLIT, bool FUSE_PREV, bool NEXT>
 __global__ void __launch_bounds__(NODE_THREADS, 2)
 node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char *__restrict__ img_head,
                  const float *__restrict__ state_prev, const float *__restrict__ Z, float *__restrict__ state_new,
-                 int n_rows, float *__restrict__ nodeT, float *__restrict__ nodeC) {
+                 int n_rows, float *__restrict__ nodeT, float *__restrict__ nodeC, int *__restrict__ wd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const float *tbias = reinterpret_cast<const float *>(smem_raw + nimg::T_BIAS);
     const float *hbias = reinterpret_cast<const float *>(smem_raw + nimg::H_BIAS);
@@ -223,12 +222,12 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
         __syncthreads();
     };
     auto wait_a = [&]() {
-        if (alive) alive = tc::mbar_wait(bars, pa, &g_node_watchdog, 1);
+        if (alive) alive = tc::mbar_wait(bars, pa, wd, 11);
         pa ^= 1u;
         tc::fence_after_sync();
     };
     auto wait_b = [&]() {
-        if (alive) alive = tc::mbar_wait(bars + 1, pb, &g_node_watchdog, 2);
+        if (alive) alive = tc::mbar_wait(bars + 1, pb, wd, 12);
         pb ^= 1u;
         tc::fence_after_sync();
     };
@@ -528,38 +527,39 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
 
 template <bool SPLIT, bool FUSE_PREV, bool NEXT>
 int launch_node_umma_variant(const void *img_tail, const void *img_head, const float *state_prev, const float *Z,
-                             float *state_new, int n_rows, float *nodeT, float *nodeC, cudaStream_t st) {
+                             float *state_new, int n_rows, float *nodeT, float *nodeC, cudaStream_t st, int *wd) {
     int n_sm = 0;
     { const int rc_ = device_setup((const void *)node_umma_kernel<SPLIT, FUSE_PREV, NEXT>, NSM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     const int n_tiles = (n_rows + 127) / 128;
     const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
     node_umma_kernel<SPLIT, FUSE_PREV, NEXT><<<grid, NODE_THREADS, NSM_TOTAL, st>>>(
-        (const unsigned char *)img_tail, (const unsigned char *)img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC);
+        (const unsigned char *)img_tail, (const unsigned char *)img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC,
+        wd ? wd : device_watchdog_word());
     PESTO_CUDA(cudaGetLastError());
     return PESTO_OK;
 }
 
 template <bool SPLIT>
 int launch_node_umma_mode(const void *img_tail, const void *img_head, const float *state_prev, const float *Z, float *state_new,
-                          int n_rows, float *nodeT, float *nodeC, cudaStream_t st) {
+                          int n_rows, float *nodeT, float *nodeC, cudaStream_t st, int *wd) {
     if (img_tail && img_head)
-        return launch_node_umma_variant<SPLIT, true, true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st);
+        return launch_node_umma_variant<SPLIT, true, true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st, wd);
     if (img_tail)
-        return launch_node_umma_variant<SPLIT, true, false>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st);
-    return launch_node_umma_variant<SPLIT, false, true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st);
+        return launch_node_umma_variant<SPLIT, true, false>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st, wd);
+    return launch_node_umma_variant<SPLIT, false, true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st, wd);
 }
 
 }  // namespace
 
 // img_tail: node image of the layer being finished (NULL: none); img_head: node image of the layer being started (NULL: none)
 int launch_node_umma(const void *img_tail, const void *img_head, const float *state_prev, const float *Z, float *state_new,
-                     int n_atoms, float *node_scratch, int mode, cudaStream_t st) {
+                     int n_atoms, float *node_scratch, int mode, cudaStream_t st, int *wd) {
     const int n_rows = n_atoms + 1;
     float *nodeT = node_scratch;
     float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
     return mode == PESTO_MODE_BF16X3
-               ? launch_node_umma_mode<true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st)
-               : launch_node_umma_mode<false>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st);
+               ? launch_node_umma_mode<true>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st, wd)
+               : launch_node_umma_mode<false>(img_tail, img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC, st, wd);
 }
 
 }  // namespace pesto

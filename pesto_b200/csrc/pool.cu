@@ -144,13 +144,15 @@ sort_segments_kernel(int n_res, const int32_t *__restrict__ off, const int32_t *
 __global__ void __launch_bounds__(256)
 residue_kernel(const float *__restrict__ hw, const float *__restrict__ state, const float *__restrict__ alog,
                const int32_t *__restrict__ off, const int32_t *__restrict__ perm, const int32_t *__restrict__ flags,
-               const int32_t *__restrict__ poison, int n_res, float *__restrict__ z) {
+               int32_t *__restrict__ poison, int n_res, float *__restrict__ z) {
     int lane = threadIdx.x & 31;
     int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n_res) return;
-    // invalid input (index out of range, membership not one-hot) cannot be reported without a host sync:
-    // poison the logits instead, the Python side turns NaN + status flags into an exception
-    if (flags[1] || (poison && (poison[0] || poison[1]))) {
+    // invalid input (index out of range, membership not one-hot) and a tensor-core stage that never completed cannot be
+    // reported without a host sync: the logits are poisoned instead; pesto_forward_status reads the flags (the Python side
+    // raises from them wherever it synchronises anyway)
+    if (flags[1] || (poison && (poison[0] || poison[1] || poison[2]))) {
+        if (flags[1] && poison && r == 0 && lane == 0) poison[3] = 1;      // residue index out of range -> status word 4
         if (lane < PESTO_NUM_OUT) z[(size_t)r * PESTO_NUM_OUT + lane] = __int_as_float(0x7fc00000);
         return;
     }
@@ -272,7 +274,7 @@ int launch_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, i
 }
 
 int launch_pool_decode(const float *head_w, const float *state, const int32_t *rid, int n_atoms, int n_res, float *z,
-                       void *scratch, const int32_t *poison, cudaStream_t st) {
+                       void *scratch, int32_t *poison, cudaStream_t st) {
     PoolScratch p = carve(scratch, n_atoms, n_res);
     PESTO_CUDA(cudaMemsetAsync(p.cnt, 0, p.zero_bytes, st));
     pool_logits_kernel<<<(n_atoms + 7) / 8, 256, 0, st>>>(head_w, state, rid, n_atoms, n_res, p.alog, p.cnt, p.flags);

@@ -126,7 +126,8 @@ void pack_tc_layer(const float *blob, void *dst_v) {
 
 namespace {
 
-__device__ int g_tc_watchdog = 0;     // != 0: a tensor-core stage timed out (stage id), see mbar_wait
+__device__ int g_tc_watchdog = 0;     // UMMA probe only: != 0 = its tensor-core stage timed out
+__device__ int g_tc_debug = 0;        // pesto_debug_force_watchdog: bit 0 = the third-layer GEMMs are never committed (a "hung" stage)
 
 constexpr int HALF_THREADS = 256;     // one tile pipeline: 8 warps = two column groups x four TMEM lane quarters
 constexpr int CTA_THREADS = 2 * HALF_THREADS;
@@ -318,7 +319,10 @@ template <int NN, bool SPLIT>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t *__restrict__ ids32,
                const float4 *__restrict__ geom, const float *__restrict__ state_in, const float *__restrict__ nodeT,
-               const float *__restrict__ nodeC, float *__restrict__ Zout, long long *__restrict__ prof, int prof_tiles) {
+               const float *__restrict__ nodeC, float *__restrict__ Zout, long long *__restrict__ prof, int prof_tiles,
+               int *__restrict__ wd) {
+    // wd: status word of the forward (or the device's fallback word): a tensor-core stage that never completes records its
+    // id there, and the forward's last kernel turns a non-zero word into NaN logits -- a hung MMA is never silent
     constexpr int TA = 128 / NN;                    // atoms per tile
     constexpr int SEG = NN < 32 ? NN : 32;          // lanes of one atom inside a warp
     constexpr int WPA = NN / SEG;                   // warps (of one group) per atom: 2 for nn = 64
@@ -384,7 +388,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int bar_id = 1 + H, bar_g0 = 3 + H;
     uint32_t ph0 = 0, ph1 = 0;               // parities of this thread's two chunk barriers (2 grp, 2 grp + 1)
     uint64_t *bar0 = bars + 2 * grp, *bar1 = bar0 + 1;
-    bool alive = true;      // false after a tensor-core stage timed out: finish with garbage, but finish
+    bool alive = true;      // false after a tensor-core stage timed out: finish with garbage (flagged through wd), but finish
+    const int dbg = g_tc_debug;
+    const uint32_t max_spin = dbg ? 1u << 6 : 1u << 20;
     PairConsts kc;
     kc.neg1 = pk2(-1.f, -1.f);
     kc.c = pk2(LOG2E, LOG2E);
@@ -688,7 +694,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     }
                 }
             }
-            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 1);
+            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, wd, 1, max_spin);
             tc::fence_after_sync();
             estage_finish<SPLIT, (NN >= 16)>(tlane + TX + 32 * c, y, kc);
         }
@@ -728,7 +734,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
                 for (int kr = 0; kr < 4; ++kr) { y[bk][kr][0] = bb.x; y[bk][kr][1] = bb.y; }
             }
-            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, &g_tc_watchdog, 2);
+            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, wd, 2, max_spin);
             tc::fence_after_sync();
             estage_finish<SPLIT, (NN >= 16)>(tlane + TY + 32 * c, y, kc);
         }
@@ -742,8 +748,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             tc::fence_after_sync();
             issue_gemm<SPLIT, 2, 16, 16, tcimg::B3Q>(tbase, TX + 0, TY + 0, 16, img14);
             issue_gemm<SPLIT, 2, 16, 16, tcimg::B3P>(tbase, TX + 16, TY + 32, 16, img14);
-            tc::umma_commit(bars_u + 0);
-            tc::umma_commit(bars_u + 1);                                 // (keeps three phases per tile on every barrier)
+            if (!(dbg & 1)) {
+                tc::umma_commit(bars_u + 0);
+                tc::umma_commit(bars_u + 1);                             // (keeps three phases per tile on every barrier)
+            }
         }
         if (hwarp_u == 4 && tc::elect_one()) {
             tc::fence_after_sync();
@@ -787,7 +795,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #ifdef PESTO_X_PJR2
         PJR_LOAD();
 #endif
-        if (alive) alive = tc::mbar_wait(bar0, ph0, &g_tc_watchdog, 3);     // group 0: Kq | Kp; group 1: V0
+        if (alive) alive = tc::mbar_wait(bar0, ph0, wd, 3, max_spin);     // group 0: Kq | Kp; group 1: V0
         tc::fence_after_sync();
         PROF_STAMP(10);
 
@@ -859,8 +867,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (half == 1) {
-                    if (alive) alive = tc::mbar_wait(bar1, ph1, &g_tc_watchdog, 3);
-                    if (S0SPLIT && alive) alive = tc::mbar_wait(bars + 1, ph1, &g_tc_watchdog, 3);      // ... and Kq | Kp: Y is free
+                    if (alive) alive = tc::mbar_wait(bar1, ph1, wd, 3, max_spin);
+                    if (S0SPLIT && alive) alive = tc::mbar_wait(bars + 1, ph1, wd, 3, max_spin);      // ... and Kq | Kp: Y is free
                     tc::fence_after_sync();
                     if (S0SPLIT) s0_store_pj();
                 }
@@ -886,7 +894,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(18);
         if (more) {
             // every MMA of M3 has read Y: each group has waited for its own GEMMs, now for the other group's last commit
-            if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, &g_tc_watchdog, 3);
+            if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, wd, 3, max_spin);
             tc::fence_after_sync();
             s0_store(tile + tstride, gn);
         }
@@ -987,38 +995,28 @@ int g_prof_tiles = 0;
 
 template <int NN, bool SPLIT>
 int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
-                   const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
+                   const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st, int *wd) {
     int n_sm = 0;
     { const int rc_ = device_setup((const void *)edge_kernel_tc<NN, SPLIT>, SM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     constexpr int TA = 128 / NN;
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
+    if (!wd) wd = device_watchdog_word();
     edge_kernel_tc<NN, SPLIT><<<grid, CTA_THREADS, SM_TOTAL, st>>>((const unsigned char *)tcw, n_atoms, ids32,
                                                                  (const float4 *)geom, state_in, nodeT, nodeC, Zout,
-                                                                 g_prof_buf, g_prof_tiles);
+                                                                 g_prof_buf, g_prof_tiles, wd);
     PESTO_CUDA(cudaGetLastError());
-    if (getenv("PESTO_TC_DEBUG")) {       // debugging aid: synchronise and report a timed-out tensor-core stage
-        PESTO_CUDA(cudaStreamSynchronize(st));
-        int wd = 0;
-        PESTO_CUDA(cudaMemcpyFromSymbol(&wd, g_tc_watchdog, sizeof(int)));
-        if (wd) {
-            int zero = 0;
-            cudaMemcpyToSymbol(g_tc_watchdog, &zero, sizeof(int));
-            set_error("edge_kernel_tc<%d>: tensor-core stage M%d never completed (watchdog)", NN, wd);
-            return PESTO_ECUDA;
-        }
-    }
     return PESTO_OK;
 }
 
 template <bool SPLIT>
 int dispatch_tc(int nn, const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
-                const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st) {
+                const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st, int *wd) {
     switch (nn) {
-        case 8:  return launch_edge_tc<8, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 16: return launch_edge_tc<16, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 32: return launch_edge_tc<32, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
-        case 64: return launch_edge_tc<64, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st);
+        case 8:  return launch_edge_tc<8, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st, wd);
+        case 16: return launch_edge_tc<16, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st, wd);
+        case 32: return launch_edge_tc<32, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st, wd);
+        case 64: return launch_edge_tc<64, SPLIT>(tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Zout, st, wd);
         default:
             set_error("state_update: unsupported nn=%d (supported: 8, 16, 32, 64)", nn);
             return PESTO_EINVAL;
@@ -1030,7 +1028,7 @@ int dispatch_tc(int nn, const void *tcw, int n_atoms, const int32_t *ids32, cons
 // Edge kernel only: attention sums of one layer -> Z[n_atoms+1][256] (row 0 unused).  nodeT / nodeC must hold the
 // layer's per-atom factors (launch_node_fused).
 int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
-                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st) {
+                         const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st, int *wd) {
     if (!tcw) {
         set_error("state_update: tensor-core weight images are missing");
         return PESTO_ESTATE;
@@ -1038,28 +1036,28 @@ int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, 
     const int n_rows = n_atoms + 1;
     float *nodeT = node_scratch;
     float *nodeC = node_scratch + (size_t)n_rows * NODE_T_STRIDE;
-    return mode == PESTO_MODE_BF16X3 ? dispatch_tc<true>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st)
-                                     : dispatch_tc<false>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st);
+    return mode == PESTO_MODE_BF16X3 ? dispatch_tc<true>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st, wd)
+                                     : dispatch_tc<false>(nn, tcw, n_atoms, ids32, geom, state_in, nodeT, nodeC, Z, st, wd);
 }
 
 // One complete layer state_in -> state_out (staged API, three launches): head factors, edge kernel, per-atom tail.
 // `ev` (optional, 3 events): before the head kernel, between head and edge kernel, after the edge kernel.
 int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
                            const float *state_in, float *state_out, float *node_scratch, float *Z, int mode,
-                           cudaStream_t st, cudaEvent_t *ev) {
+                           cudaStream_t st, cudaEvent_t *ev, int *wd) {
     if (ev) PESTO_CUDA(cudaEventRecord(ev[0], st));
     const void *nimg = tcw ? (const void *)((const unsigned char *)tcw + tc_edge_bytes()) : nullptr;
     if (!nimg) {
         set_error("state_update: tensor-core weight images are missing");
         return PESTO_ESTATE;
     }
-    int rc = launch_node_umma(nullptr, nimg, state_in, nullptr, nullptr, n_atoms, node_scratch, mode, st);
+    int rc = launch_node_umma(nullptr, nimg, state_in, nullptr, nullptr, n_atoms, node_scratch, mode, st, wd);
     if (rc != PESTO_OK) return rc;
     if (ev) PESTO_CUDA(cudaEventRecord(ev[1], st));
-    rc = launch_edge_tc_layer(lw, tcw, nn, n_atoms, ids32, geom, state_in, node_scratch, Z, mode, st);
+    rc = launch_edge_tc_layer(lw, tcw, nn, n_atoms, ids32, geom, state_in, node_scratch, Z, mode, st, wd);
     if (rc != PESTO_OK) return rc;
     if (ev) PESTO_CUDA(cudaEventRecord(ev[2], st));
-    return launch_node_umma(nimg, nullptr, state_in, Z, state_out, n_atoms, node_scratch, mode, st);
+    return launch_node_umma(nimg, nullptr, state_in, Z, state_out, n_atoms, node_scratch, mode, st, wd);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1165,6 +1163,14 @@ extern "C" int pesto_debug_umma_probe(const float *A, const float *B, float *D, 
  * each half.  Stamp order: 0 tile start, 1 S0 done, 2 barrier, 3 (unused), 4 M1 done, 5 E1 done, 6 barrier,
  * 7 M2 done, 8 E2 done, 9 barrier, 10 M3 done, 11 E3 done, 12 barrier, 13 R loop done, 14 partial sums visible,
  * 15 Z written, 16 next T copies issued, 17 p_j prefetch issued (inside E3), 18 E3 arithmetic done. */
+/* Debug: on != 0 makes every tensor-core edge kernel skip the completion signal of its third-layer GEMMs (and shortens its
+ * waits), i.e. simulates a tensor-core stage that hangs: the kernels must finish, and the forward must report it. */
+extern "C" int pesto_debug_force_watchdog(int on) {
+    const int v = on ? 1 : 0;
+    PESTO_CUDA(cudaMemcpyToSymbol(pesto::g_tc_debug, &v, sizeof(int)));
+    return PESTO_OK;
+}
+
 extern "C" int pesto_debug_edge_timeline(void *buf, int max_tiles) {
     pesto::g_prof_buf = (long long *)buf;
     pesto::g_prof_tiles = buf ? max_tiles : 0;

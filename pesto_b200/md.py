@@ -47,4 +47,6 @@ def predict_trajectory(model, X_traj, ids_topk, q, M, frames=None, frames_per_ba
             Xb = Xb.to(dev, torch.float32, non_blocking=True).contiguous()
             z = model(Xb, ids_b[:f * n_atoms], q_b[:f * n_atoms], rid_b[:f * n_atoms], n_res=f * n_res)
             out[b0:b0 + f] = z.view(f, n_res, 5)
+            if b0 == 0 or b0 + per >= len(frames):
+                model.raise_if_failed(dev)     # input flags show on the first batch (topology and membership are shared by all frames)
     return out

@@ -87,6 +87,7 @@ class Model(torch.nn.Module):
         self.dm = _mlp(2 * config["dm"]["N0"], config["dm"]["N1"], config["dm"]["N2"])
         self._handles = {}        # device index -> C model handle
         self._workspaces = {}     # device index -> uint8 tensor
+        self._last = {}           # device index -> (aligned workspace pointer, n_atoms, n_res) of the last forward
 
     # ---- packed-weight handle management ------------------------------------------------------------------
     def _invalidate(self):
@@ -188,7 +189,28 @@ class Model(torch.nn.Module):
                                    _lib.ptr(rid), n_atoms, n_res, z.data_ptr(), aligned, ws.numel() - (aligned - base),
                                    _lib.MODES[mode or self.mode], ctypes.c_void_p(stream))
             _lib.check(rc, "pesto_forward")
-        return z if out_device == dev else z.to(out_device)
+            self._last[dev.index] = (aligned, n_atoms, n_res)
+        if out_device != dev:
+            z = z.to(out_device)
+            self.raise_if_failed(dev)          # the copy synchronised anyway
+        return z
+
+    def raise_if_failed(self, device=None):
+        """Errors only the device can detect (a neighbour id or residue index out of range, a row of M that is not one-hot,
+        a tensor-core stage that never completed) make every logit of that forward NaN without a host synchronisation.
+        This reads the status words of the last forward on `device` (synchronising its current stream) and raises
+        PestoError if one is set.  Callers that synchronise anyway -- the structure runner, the trajectory and apply paths --
+        call it there, as the reference's callers catch exceptions per structure (interfaceome/apply_model.py:81-82)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        last = self._last.get(idx)
+        if last is None:
+            return
+        status = (ctypes.c_int32 * 8)()
+        with torch.cuda.device(idx):
+            stream = torch.cuda.current_stream(idx).cuda_stream
+            rc = _lib.load().pesto_forward_status(ctypes.c_void_p(last[0]), last[1], last[2], status, ctypes.c_void_p(stream))
+        _lib.check(rc, "pesto_forward")
 
     def launches_per_forward(self, dense_m=True):
         return len(self.config["sum"]) * 2 + 3 + 5 + (1 if dense_m else 0) + (0 if self.mode == "fp32" else 1)

@@ -130,6 +130,7 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
             done.record(main)
             nxt = stage(k + 1) if k + 1 < len(batches) else None      # host work of the next batch under this batch's GPU work
             done.synchronize()
+            model.raise_if_failed(dev)         # device-side flags of this batch's forward (bad ids, hung tensor-core stage) -> PestoError
             r0 = 0
             for i, nr in zip(b, n_rs):
                 yield i, zh[r0:r0 + nr].clone()

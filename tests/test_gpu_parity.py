@@ -322,14 +322,49 @@ def test_bad_inputs_raise_or_poison(cuda_models):
     with pytest.raises(_lib.PestoError):
         model(X.cuda(), ids[:, :32].contiguous(), q0, M)           # fewer columns than the largest nn
     bad = ids.clone()
-    bad[5, 5] = 4000                                               # out of range -> NaN logits, no crash
+    bad[5, 5] = 4000                                               # out of range -> NaN logits, no crash, and a status flag
     assert torch.isnan(model(X.cuda(), bad, q0, M)).all()
+    with pytest.raises(_lib.PestoError, match="neighbour id"):
+        model.raise_if_failed()
     M2 = M.clone()
     M2[3] = 0.0                                                    # not one-hot -> NaN logits
     assert torch.isnan(model(X.cuda(), ids, q0, M2)).all()
+    with pytest.raises(_lib.PestoError, match="one-hot"):
+        model.raise_if_failed()
+    rid_bad = torch.zeros(128, dtype=torch.int32, device="cuda")
+    rid_bad[7] = 99                                                # residue index >= n_res
+    assert torch.isnan(model(X.cuda(), ids, q0, rid_bad, n_res=4)).all()
+    with pytest.raises(_lib.PestoError, match="residue index"):
+        model.raise_if_failed()
+    with pytest.raises(_lib.PestoError):                           # CPU tensors in: the result copy synchronises, so it raises directly
+        model(X, bad.cpu(), q0.cpu(), M.cpu())
     assert torch.isfinite(model(X.cuda(), ids, q0, M)).all()       # and the model still works afterwards
+    model.raise_if_failed()
     with pytest.raises(ValueError):                                # empty structure: the reference raises too (max of empty)
         model(X[:0].cuda(), ids[:0], q0[:0], M[:0])
+
+
+def test_hung_tensor_core_stage_is_reported(cuda_models):
+    """A tcgen05 stage whose completion never arrives (simulated: the edge kernels skip the commit of their third-layer
+    GEMMs) must neither hang the GPU nor pass silently: the kernels' bounded waits give up, the forward's status word
+    carries the stage id, every logit is NaN and raise_if_failed raises."""
+    from pesto_b200 import _lib
+    lib = _lib.load()
+    model = cuda_models("i_v4_0", "f16x3")
+    c = load_case("synth517")
+    assert torch.isfinite(run_case(model, c, mode="f16x3")).all()
+    _lib.check(lib.pesto_debug_force_watchdog(1), "force watchdog")
+    try:
+        z = run_case(model, c, mode="f16x3")
+        torch.cuda.synchronize()
+        assert torch.isnan(z).all()
+        with pytest.raises(_lib.PestoError, match="tensor-core stage 3"):
+            model.raise_if_failed()
+    finally:
+        _lib.check(lib.pesto_debug_force_watchdog(0), "force watchdog off")
+    z = run_case(model, c, mode="f16x3")
+    model.raise_if_failed()
+    assert (z.cpu() - torch.from_numpy(c["z_i_v4_0"])).abs().max().item() <= 3e-4
 
 
 # ------------------------------------------------------------------------------------------------- tensor-core modes
