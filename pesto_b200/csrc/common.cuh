@@ -129,6 +129,24 @@ int *device_watchdog_word();
         if (_rc != PESTO_OK) return _rc;                             \
     } while (0)
 
+// Launch `kernel` on `st` with programmatic dependent launch allowed: its CTAs may start while the previous kernel of the
+// stream is finishing and run until their griddepcontrol.wait (tc::pdl_wait); everything before that point must depend on
+// the model only.  Kernels that never execute pdl_wait / pdl_launch_dependents behave as under a normal launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // launch wrappers implemented in the individual .cu files
 int launch_knn(const float *X, int n_atoms, const int32_t *seg_off, int n_seg, int k, int base,
                int64_t *ids_out, float *d_out, float *r_out, void *scratch, cudaStream_t st);

@@ -111,7 +111,7 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr int NODE_THREADS = 128;
 constexpr uint32_t NT_COLS = 256;                 // TMEM columns per CTA
 constexpr uint32_t A0 = 0, A1 = 64, DC = 128;     // operand regions (64 columns each) and accumulator region (128)
-constexpr int NSM_BAR = nimg::TOTAL;              // 2 mbarriers + TMEM slot
+constexpr int NSM_BAR = nimg::TOTAL;              // 2 mbarriers + TMEM slot (+16) + weight-image barrier (+24)
 constexpr int NSM_TOTAL = NSM_BAR + 32;
 
 // ELU without a branch: max(x, 0) + (exp(min(x, 0)) - 1), one MUFU.EX2 (the edge kernel's formulation)
@@ -193,21 +193,23 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int m = lane & 3, rl = lane >> 2;
     if (warp == 0) tc::tmem_alloc(tmem_slot, NT_COLS);
+    // Prologue = model data only (weight images through the TMA engine, barriers, TMEM): under programmatic dependent launch
+    // it overlaps the tail of the previous kernel of the forward; pdl_wait below is where that kernel's outputs are needed.
+    uint64_t *wbar = bars + 3;
     if (t == 0) {
         tc::mbar_init(bars, 1);
         tc::mbar_init(bars + 1, 1);
+        tc::mbar_init(wbar, (FUSE_PREV ? 1 : 0) + (NEXT ? 1 : 0));
         tc::fence_mbar_init();
+        if (FUSE_PREV) tc::bulk_g2s_block(smem_raw, img_tail, nimg::T_BYTES, wbar);
+        if (NEXT) tc::bulk_g2s_block(smem_raw + nimg::T_BYTES, img_head + nimg::T_BYTES, nimg::H_BYTES, wbar);
     }
-    if (FUSE_PREV)
-        for (int u = t; u < nimg::T_BYTES / 16; u += NODE_THREADS)
-            reinterpret_cast<uint4 *>(smem_raw)[u] = __ldg(reinterpret_cast<const uint4 *>(img_tail) + u);
-    if (NEXT)
-        for (int u = t; u < nimg::H_BYTES / 16; u += NODE_THREADS)
-            reinterpret_cast<uint4 *>(smem_raw + nimg::T_BYTES)[u] = __ldg(reinterpret_cast<const uint4 *>(img_head + nimg::T_BYTES) + u);
-    tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::mbar_wait(wbar, 0, wd, 17);
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int warp_u = __shfl_sync(FULLM, warp, 0);
     const uint32_t tbase = __shfl_sync(FULLM, *tmem_slot, 0);
     const uint32_t tq = tbase + ((uint32_t)(warp_u * 32) << 16);     // warp-uniform: TMEM addresses stay in uniform registers
@@ -532,10 +534,9 @@ int launch_node_umma_variant(const void *img_tail, const void *img_head, const f
     { const int rc_ = device_setup((const void *)node_umma_kernel<SPLIT, FUSE_PREV, NEXT>, NSM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     const int n_tiles = (n_rows + 127) / 128;
     const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
-    node_umma_kernel<SPLIT, FUSE_PREV, NEXT><<<grid, NODE_THREADS, NSM_TOTAL, st>>>(
-        (const unsigned char *)img_tail, (const unsigned char *)img_head, state_prev, Z, state_new, n_rows, nodeT, nodeC,
-        wd ? wd : device_watchdog_word());
-    PESTO_CUDA(cudaGetLastError());
+    PESTO_CUDA(launch_pdl(node_umma_kernel<SPLIT, FUSE_PREV, NEXT>, dim3(grid), dim3(NODE_THREADS), NSM_TOTAL, st,
+                          (const unsigned char *)img_tail, (const unsigned char *)img_head, state_prev, Z, state_new, n_rows, nodeT,
+                          nodeC, wd ? wd : device_watchdog_word()));
     return PESTO_OK;
 }
 

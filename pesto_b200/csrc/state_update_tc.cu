@@ -347,13 +347,17 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 80);
 
     if (tid < 32) tc::tmem_alloc(tmem_slot, TM_COLS);
+    // Prologue = everything that depends on the model only (weight images, barriers, TMEM): under programmatic dependent
+    // launch it runs while the previous kernel of the forward is still finishing (see pdl_wait below).  The images come
+    // through the TMA engine (one thread, four bulk copies, completion on wbar).
+    uint64_t *wbar = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR + 88);
     if (tid == 0) {
         for (int b = 0; b < 10; ++b)
             tc::mbar_init(reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + b, b % 5 == 4 ? HALF_THREADS : 1);
+        tc::mbar_init(wbar, 1);
         tc::fence_mbar_init();
+        tc::bulk_g2s_block(img, tcw, tcimg::TOTAL, wbar);
     }
-    for (int u = tid; u < tcimg::TOTAL / 16; u += CTA_THREADS)
-        reinterpret_cast<uint4 *>(img)[u] = __ldg(reinterpret_cast<const uint4 *>(tcw) + u);
     {   // rows k = 64..79 of B1 -> the per-half, per-tile mutable copy: row 64 = W_d (hi plane), rows 65..76 = U planes
         // (per tile), row 77 = W_d (lo plane; the distance enters twice, so this K step needs no lo-plane MMA)
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(tcw + tcimg::B1 + 8 * 2048) + ht);
@@ -377,6 +381,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::mbar_wait(wbar, 0, wd, 7);            // weight images have landed
+    tc::pdl_launch_dependents();              // the next kernel (per-atom kernel) may start its own prologue on free SMs
+    tc::pdl_wait();                           // from here on: data of the previous kernels (per-atom factors, state, topology)
     // warp-uniform copies (shuffles from lane 0 let the compiler keep them in uniform registers: the MMA issue code
     // then needs no per-instruction vote / broadcast)
     const int hwarp_u = __shfl_sync(FULLM, hwarp, 0), H_u = __shfl_sync(FULLM, H, 0);
@@ -1002,10 +1009,8 @@ int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const flo
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
     if (!wd) wd = device_watchdog_word();
-    edge_kernel_tc<NN, SPLIT><<<grid, CTA_THREADS, SM_TOTAL, st>>>((const unsigned char *)tcw, n_atoms, ids32,
-                                                                 (const float4 *)geom, state_in, nodeT, nodeC, Zout,
-                                                                 g_prof_buf, g_prof_tiles, wd);
-    PESTO_CUDA(cudaGetLastError());
+    PESTO_CUDA(launch_pdl(edge_kernel_tc<NN, SPLIT>, dim3(grid), dim3(CTA_THREADS), SM_TOTAL, st, (const unsigned char *)tcw, n_atoms,
+                          ids32, (const float4 *)geom, state_in, nodeT, nodeC, Zout, g_prof_buf, g_prof_tiles, wd));
     return PESTO_OK;
 }
 

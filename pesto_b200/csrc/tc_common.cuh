@@ -171,6 +171,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// A contiguous block global -> shared through the TMA engine (SASS UBLKCP), issued by ONE thread: arms `bar` with the byte
+// count and splits the block into pieces of at most 32 KB; the block's readers wait for the barrier's phase.
+__device__ __forceinline__ void bulk_g2s_block(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    mbar_arrive_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u)
+        bulk_g2s(reinterpret_cast<unsigned char *>(dst_smem) + o, reinterpret_cast<const unsigned char *>(src_gmem) + o,
+                 bytes - o < 32768u ? bytes - o : 32768u, bar);
+}
+
+// ---- programmatic dependent launch (the launch carries cudaLaunchAttributeProgrammaticStreamSerialization) ---------------
+// pdl_wait: everything the previous kernel in the stream wrote is visible afterwards (no-op for a normal launch);
+// pdl_launch_dependents: the next kernel's CTAs may start (on SMs with room) and run their prologue up to their own pdl_wait
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- cp.async (LDGSTS): 16 bytes global -> shared per lane, L2 only -------------------------------------------------
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
