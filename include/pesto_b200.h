@@ -150,9 +150,13 @@ int    pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1
  * workspace and make every logit NaN.  pesto_forward_status copies the PESTO_STATUS_WORDS words of the forward that
  * last used `workspace` (same n_atoms, n_res) to status_host, synchronising `stream`, and returns PESTO_EINPUT
  * ([1] a neighbour id out of range, [2] a row of M not one-hot, [4] a residue index out of range) or PESTO_ECUDA
- * ([3] = id of a tensor-core stage whose completion never arrived: the kernels' bounded waits gave up) with
+ * ([3] = id of a tensor-core stage whose completion never arrived: the kernels' bounded waits gave up; [3] = 100: the
+ * state left the range the fp16 operand planes of the tensor-core modes cover, |q| or |p| > 2^14 -> PESTO_EINPUT) with
  * pesto_last_error() set; PESTO_OK if the forward was clean.  Callers that synchronise anyway (to read z) call it there. */
 int pesto_forward_status(const void *workspace, int n_atoms, int n_res, int32_t *status_host, void *stream);
+/* byte offset of those status words inside the workspace (callers that pipeline forwards copy the words out with the
+ * logits, before the next forward on the same workspace clears them) */
+size_t pesto_forward_status_offset(int n_atoms, int n_res);
 
 /* Debug: simulate a hung tensor-core stage (on != 0: the edge kernels never signal their third-layer GEMMs and wait only
  * briefly); pesto_debug_watchdog reads and clears the device word that staged calls (pesto_state_update) report into. */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pesto_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pesto_forward_launch_count": (_i, [_vp, _i, _i]),
     "pesto_forward_status": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pesto_forward_status_offset": (_sz, [_i, _i]),
     "pesto_debug_force_watchdog": (_i, [_i]),
     "pesto_debug_watchdog": (_i, [_vp]),
     "pesto_pdb_count_atoms_host": (_i, [_c.c_char_p, _sz]),
@@ -74,6 +75,22 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+STATUS_MESSAGES = {1: "a neighbour id in ids_topk is out of range [0, n_atoms]", 2: "a row of the membership matrix M is not one-hot",
+                   4: "a residue index is out of range [0, n_res)"}
+
+
+def raise_status(words, what="pesto_forward"):
+    """Raise PestoError if the status words of a forward (PESTO_STATUS_WORDS int32, word 0 is scratch) flag an error."""
+    for k, msg in STATUS_MESSAGES.items():
+        if int(words[k]):
+            raise PestoError(f"{what}: {msg} (the logits are NaN)")
+    if int(words[3]) >= 100:
+        raise PestoError(f"{what}: the state left the range of the fp16 operand planes (|q| or |p| > 2^14, or NaN): run this model / "
+                         "input in mode fp32 (the logits are NaN)")
+    if int(words[3]):
+        raise PestoError(f"{what}: tensor-core stage {int(words[3])} never completed (watchdog): the logits are NaN")
 
 
 def check(rc, what):

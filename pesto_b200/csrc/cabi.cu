@@ -490,6 +490,12 @@ int pesto_forward(const pesto_model_t *m, const float *X, const int64_t *ids1, i
     return launch_pool_decode(m->head(), cur, rid_dev, n_atoms, n_res, z, w.pool, w.status + 1, st);
 }
 
+size_t pesto_forward_status_offset(int n_atoms, int n_res) {
+    if (n_atoms < 1 || n_res < 1) return 0;
+    char *fake = reinterpret_cast<char *>(uintptr_t(1) << 20);
+    return (size_t)(reinterpret_cast<char *>(carve_workspace(fake, n_atoms, n_res).status) - fake);
+}
+
 int pesto_forward_status(const void *workspace, int n_atoms, int n_res, int32_t *status_host, void *stream) {
     if (!workspace || !status_host || n_atoms < 1 || n_res < 1) {
         set_error("pesto_forward_status: null pointer or bad sizes");
@@ -503,6 +509,11 @@ int pesto_forward_status(const void *workspace, int n_atoms, int n_res, int32_t 
     if (status_host[1]) { set_error("pesto_forward: a neighbour id in ids_topk is out of range [0, n_atoms]"); return PESTO_EINPUT; }
     if (status_host[2]) { set_error("pesto_forward: a row of the membership matrix M is not one-hot"); return PESTO_EINPUT; }
     if (status_host[4]) { set_error("pesto_forward: a residue index is out of range [0, n_res)"); return PESTO_EINPUT; }
+    if (status_host[3] >= 100) {
+        set_error("pesto_forward: the state left the range of the fp16 operand planes (|q| or |p| > 2^14, or NaN): run this "
+                  "model / input in mode fp32; the logits are NaN");
+        return PESTO_EINPUT;
+    }
     if (status_host[3]) {
         set_error("pesto_forward: tensor-core stage %d never completed (watchdog): the logits are NaN", status_host[3]);
         return PESTO_ECUDA;

@@ -216,6 +216,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
     const uint32_t sb = tc::smem_u32(smem_raw);
     uint32_t pa = 0, pb = 0;
     bool alive = true;
+    float big = 0.f;      // max over this thread's state entries of |q| and |p|^2 (fp16 operand range check, see the kernel's end)
 
     // block barrier between "operand written / accumulator read" and the next MMA issue
     auto sync_tmem = [&]() {
@@ -392,7 +393,10 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                     *reinterpret_cast<float2 *>(dq + 8) = make_float2(q[k][2], q[k][3]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pn2[k][u] = 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    pn2[k][u] = 0.f;
+                    big = fmaxf(big, q[k][u] * q[k][u]);
+                }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -425,6 +429,7 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
                 store_a8<SPLIT>(tq + A0 + 8 * g, tq + A0 + 32 + 8 * g, hi, lo);                 // q: K positions 0..31
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    big = fmaxf(fmaxf(big, fmaxf(pn2[k][0], pn2[k][1])), fmaxf(pn2[k][2], pn2[k][3]));
                     nsplit<SPLIT>(n_sqrt(pn2[k][0]), n_sqrt(pn2[k][1]), hi[k][0], lo[k][0]);     // |p| (:105)
                     nsplit<SPLIT>(n_sqrt(pn2[k][2]), n_sqrt(pn2[k][3]), hi[k][1], lo[k][1]);
                 }
@@ -522,6 +527,11 @@ node_umma_kernel(const unsigned char *__restrict__ img_tail, const unsigned char
         __syncthreads();                                         // all TMEM reads of this tile precede the next tile's stores
         tc::fence_after_sync();
     }
+    // The tensor-core modes convert the state, its per-atom factors and the edge activations to fp16 planes with saturation
+    // (65504).  The shipped checkpoints keep |state| below ~50; a state beyond 2^14 is outside the range these planes were
+    // validated for, so it is flagged (code 100 in the forward's watchdog word -> NaN logits, PestoError "use mode fp32")
+    // instead of silently saturating somewhere downstream.
+    if (big > 16384.f * 16384.f || !(big == big)) atomicMax(wd, 100);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, NT_COLS);

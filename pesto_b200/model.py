@@ -189,11 +189,21 @@ class Model(torch.nn.Module):
                                    _lib.ptr(rid), n_atoms, n_res, z.data_ptr(), aligned, ws.numel() - (aligned - base),
                                    _lib.MODES[mode or self.mode], ctypes.c_void_p(stream))
             _lib.check(rc, "pesto_forward")
-            self._last[dev.index] = (aligned, n_atoms, n_res)
+            self._last[dev.index] = (aligned, n_atoms, n_res, ws, aligned - base)
         if out_device != dev:
             z = z.to(out_device)
             self.raise_if_failed(dev)          # the copy synchronised anyway
         return z
+
+    def status_words(self, device=None):
+        """int32[8] device view of the status words of the last forward on `device` (stream-ordered: valid until the next
+        forward on that device starts).  Callers that keep several forwards in flight copy it out together with the logits
+        and hand the host copy to `_lib.raise_status`."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        _, n_atoms, n_res, ws, shift = self._last[idx]
+        off = shift + _lib.load().pesto_forward_status_offset(n_atoms, n_res)
+        return ws[off:off + 32].view(torch.int32)
 
     def raise_if_failed(self, device=None):
         """Errors only the device can detect (a neighbour id or residue index out of range, a row of M that is not one-hot,

@@ -9,6 +9,7 @@ src/dataset.py:101-110), and -- across GPUs -- sharded by cost with no data-path
 import numpy as np
 import torch
 
+from . import _lib
 from .data_encoding import batch_topology, onehot, std_elements
 
 TARGET_ATOMS_PER_BATCH = 131072
@@ -89,8 +90,10 @@ class _PinnedSlot:
 def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATOMS_PER_BATCH, num_nn=64):
     """Yield (index, z[n_res, 5] float32 on the host) for every structure dictionary (keys xyz, element, resid), in order.
 
-    Pipeline per batch k: (1) its kNN + forward + logits D2H are enqueued, (2) the host encodes batch k+1 and enqueues
-    its pinned H2D copies on a copy stream while the GPU works, (3) the host waits for batch k's logits."""
+    Pipeline per batch k: (1) its kNN + forward + D2H of logits and status words are enqueued, (2) the host encodes batch
+    k+1 and enqueues its pinned H2D copies on a copy stream while the GPU works, (3) the host collects batch k-1's results
+    -- two batches are in flight, so the GPU never waits for the host between batches.  Errors only the device can see
+    (a neighbour id or residue index out of range, a hung tensor-core stage) raise PestoError for the batch they occur in."""
     dev = torch.device(device)
     sizes = [len(s["xyz"]) for s in structures]
     batches = pack_batches(sizes, target_atoms, num_nn)
@@ -112,7 +115,19 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
         return on_dev, slot.copied, n_at, n_rs
 
     nxt = stage(0) if batches else None
-    zpin = [None, None]
+    zpin, spin = [None, None], [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def finish(job):            # wait for a batch's logits and status words, hand out per-structure results
+        k, b, n_rs, zh, done = job
+        done.synchronize()
+        _lib.raise_status(spin[k % 2].numpy(), "predict_structures")     # bad ids / hung tensor-core stage of THIS batch -> PestoError
+        zc = zh.clone()
+        r0 = 0
+        for i, nr in zip(b, n_rs):
+            yield i, zc[r0:r0 + nr]
+            r0 += nr
+
+    pending = None              # two batches in flight: batch k's results are collected while batch k + 1 runs
     with torch.no_grad():
         for k, b in enumerate(batches):
             (Xd, q0d, ridd), ready, n_at, n_rs = nxt
@@ -126,12 +141,12 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
                 zpin[k % 2] = torch.empty((z.shape[0] * 5 // 4, 5), dtype=torch.float32).pin_memory()
             zh = zpin[k % 2][:z.shape[0]]
             zh.copy_(z, non_blocking=True)
+            spin[k % 2].copy_(model.status_words(dev), non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
             nxt = stage(k + 1) if k + 1 < len(batches) else None      # host work of the next batch under this batch's GPU work
-            done.synchronize()
-            model.raise_if_failed(dev)         # device-side flags of this batch's forward (bad ids, hung tensor-core stage) -> PestoError
-            r0 = 0
-            for i, nr in zip(b, n_rs):
-                yield i, zh[r0:r0 + nr].clone()
-                r0 += nr
+            if pending is not None:
+                yield from finish(pending)
+            pending = (k, b, n_rs, zh, done)
+        if pending is not None:
+            yield from finish(pending)

@@ -23,7 +23,7 @@ def main():
         os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
         for name in args:
             env = dict(os.environ, PESTO_B200_LIB=os.path.join(REPO, "pesto_b200", f"libpesto_b200.{name}.so"))
-            r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline"],
+            r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-extras"],
                                env=env, capture_output=True, text=True, timeout=600)
             try:
                 d = json.loads(r.stdout.strip().splitlines()[-1])

@@ -367,6 +367,29 @@ def test_hung_tensor_core_stage_is_reported(cuda_models):
     assert (z.cpu() - torch.from_numpy(c["z_i_v4_0"])).abs().max().item() <= 3e-4
 
 
+def test_state_beyond_fp16_operand_range_is_flagged(cuda_models):
+    """The tensor-core modes convert the state and the edge activations to fp16 planes with saturation; a state outside the
+    validated range (|q| or |p| > 2^14; the shipped checkpoints stay below ~50) is flagged by the per-atom kernel instead of
+    saturating silently: code 100 in the watchdog word (staged API: the device's fallback word)."""
+    import ctypes
+    from pesto_b200 import _lib
+    model = cuda_models("i_v4_0", "f16x3")
+    lib, h, n, st0, ids32, geom, node = _staged(model, load_case("synth517"))
+    out = torch.empty_like(st0)
+    word = ctypes.c_int32(0)
+    _lib.check(lib.pesto_debug_watchdog(ctypes.byref(word)), "clear")
+    _lib.check(lib.pesto_state_update(h, 0, n, ids32.data_ptr(), geom.data_ptr(), st0.data_ptr(), out.data_ptr(), node.data_ptr(), 1, None), "layer")
+    torch.cuda.synchronize()
+    _lib.check(lib.pesto_debug_watchdog(ctypes.byref(word)), "read")
+    assert word.value == 0
+    big = st0.clone()
+    big[17, 40] = 3.0e4                                            # one vector-state entry beyond 2^14
+    _lib.check(lib.pesto_state_update(h, 0, n, ids32.data_ptr(), geom.data_ptr(), big.data_ptr(), out.data_ptr(), node.data_ptr(), 1, None), "layer")
+    torch.cuda.synchronize()
+    _lib.check(lib.pesto_debug_watchdog(ctypes.byref(word)), "read")
+    assert word.value == 100
+
+
 # ------------------------------------------------------------------------------------------------- tensor-core modes
 def _staged(model, c):
     """prologue through the staged C ABI; returns what pesto_state_update needs."""
