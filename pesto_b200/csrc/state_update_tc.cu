@@ -315,7 +315,7 @@ __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2]
 // in shared memory and interleave on the SM's four schedulers: while one half waits for the tensor core or a
 // gather, the other runs its CUDA-core stage.  Inside a half, warps 0-3 (group 0) and 4-7 (group 1) both map
 // thread -> edge / TMEM lane 32 * (warp % 4) + lane and split the columns of every stage.
-template <int NN, bool SPLIT>
+template <int NN, bool SPLIT, bool PROF>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t *__restrict__ ids32,
                const float4 *__restrict__ geom, const float *__restrict__ state_in, const float *__restrict__ nodeT,
@@ -388,13 +388,14 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     // then needs no per-instruction vote / broadcast)
     const int hwarp_u = __shfl_sync(FULLM, hwarp, 0), H_u = __shfl_sync(FULLM, H, 0);
     const uint32_t tbase = __shfl_sync(FULLM, *tmem_slot, 0) + (uint32_t)H_u * 256u;
-    const uint32_t tlane = tbase + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tlane = tbase + ((uint32_t)((hwarp_u & 3) * 32) << 16);        // (warp-uniform: TMEM addresses stay in uniform registers)
     const uint32_t img14 = tc::smem_u32(smem_raw) >> 4;                     // operand descriptors: base in 16-byte units
     const uint32_t ext14 = img14 + ((SM_HALF0 + (uint32_t)H_u * HS_BYTES + HS_EXT_HI) >> 4);
     uint64_t *bars_u = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H_u;
     const int bar_id = 1 + H, bar_g0 = 3 + H;
     uint32_t ph0 = 0, ph1 = 0;               // parities of this thread's two chunk barriers (2 grp, 2 grp + 1)
     uint64_t *bar0 = bars + 2 * grp, *bar1 = bar0 + 1;
+    const uint32_t bars_a = tc::smem_u32(bars), bar0_a = bars_a + 16u * (uint32_t)grp, bar1_a = bar0_a + 8u;      // shared-window addresses
     bool alive = true;      // false after a tensor-core stage timed out: finish with garbage (flagged through wd), but finish
     const int dbg = g_tc_debug;
     const uint32_t max_spin = dbg ? 1u << 6 : 1u << 20;
@@ -408,11 +409,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const int a_loc = e / NN, k = e % NN;
     const int tile0 = (int)blockIdx.x * 2 + H, tstride = (int)gridDim.x * 2;
     // optional phase timeline (debug): CTA 0, first thread of each group of each half, PROF_STAMPS clock stamps per tile
-    const bool profiling = prof != nullptr && blockIdx.x == 0 && (ht & 127) == 0;
+    // (PROF is a compile-time switch: even predicated off, the 19 stamps cost ~110 issue slots per tile and thread)
+    const bool profiling = PROF && prof != nullptr && blockIdx.x == 0 && (ht & 127) == 0;
     int prof_seq = 0;
 #define PROF_STAMP(kk)                                                                                          \
     do {                                                                                                         \
-        if (profiling && prof_seq < prof_tiles) prof[((size_t)prof_seq * 4 + H * 2 + grp) * PROF_STAMPS + (kk)] = clock64(); \
+        if (PROF && profiling && prof_seq < prof_tiles) prof[((size_t)prof_seq * 4 + H * 2 + grp) * PROF_STAMPS + (kk)] = clock64(); \
     } while (0)
     // S0 of one tile in two parts.  s0_compute: gather + A1 = [p_j.r | p_i.r] as packed bf16 words in registers (s0h / s0l)
     // and the U_i values; s0_store: words -> TMEM (Y), [d, 1(a), d] columns, U planes -> B1's spare K rows.  S0 runs one
@@ -701,7 +703,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     }
                 }
             }
-            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, wd, 1, max_spin);
+            if (alive) alive = tc::mbar_wait_a(cc ? bar1_a : bar0_a, cc ? ph1 : ph0, wd, 1, max_spin);
             tc::fence_after_sync();
             estage_finish<SPLIT, (NN >= 16)>(tlane + TX + 32 * c, y, kc);
         }
@@ -741,7 +743,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
                 for (int kr = 0; kr < 4; ++kr) { y[bk][kr][0] = bb.x; y[bk][kr][1] = bb.y; }
             }
-            if (alive) alive = tc::mbar_wait(cc ? bar1 : bar0, cc ? ph1 : ph0, wd, 2, max_spin);
+            if (alive) alive = tc::mbar_wait_a(cc ? bar1_a : bar0_a, cc ? ph1 : ph0, wd, 2, max_spin);
             tc::fence_after_sync();
             estage_finish<SPLIT, (NN >= 16)>(tlane + TY + 32 * c, y, kc);
         }
@@ -802,7 +804,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #ifdef PESTO_X_PJR2
         PJR_LOAD();
 #endif
-        if (alive) alive = tc::mbar_wait(bar0, ph0, wd, 3, max_spin);     // group 0: Kq | Kp; group 1: V0
+        if (alive) alive = tc::mbar_wait_a(bar0_a, ph0, wd, 3, max_spin);     // group 0: Kq | Kp; group 1: V0
         tc::fence_after_sync();
         PROF_STAMP(10);
 
@@ -874,8 +876,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (half == 1) {
-                    if (alive) alive = tc::mbar_wait(bar1, ph1, wd, 3, max_spin);
-                    if (S0SPLIT && alive) alive = tc::mbar_wait(bars + 1, ph1, wd, 3, max_spin);      // ... and Kq | Kp: Y is free
+                    if (alive) alive = tc::mbar_wait_a(bar1_a, ph1, wd, 3, max_spin);
+                    if (S0SPLIT && alive) alive = tc::mbar_wait_a(bars_a + 8u, ph1, wd, 3, max_spin);      // ... and Kq | Kp: Y is free
                     tc::fence_after_sync();
                     if (S0SPLIT) s0_store_pj();
                 }
@@ -901,7 +903,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(18);
         if (more) {
             // every MMA of M3 has read Y: each group has waited for its own GEMMs, now for the other group's last commit
-            if (alive) alive = tc::mbar_wait(bars + (grp == 0 ? 3 : 1), ph1 ^ 1u, wd, 3, max_spin);
+            if (alive) alive = tc::mbar_wait_a(bars_a + (grp == 0 ? 24u : 8u), ph1 ^ 1u, wd, 3, max_spin);
             tc::fence_after_sync();
             s0_store(tile + tstride, gn);
         }
@@ -1004,12 +1006,16 @@ template <int NN, bool SPLIT>
 int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const float *geom, const float *state_in,
                    const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st, int *wd) {
     int n_sm = 0;
-    { const int rc_ = device_setup((const void *)edge_kernel_tc<NN, SPLIT>, SM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
+    // the debug timeline (pesto_debug_edge_timeline) exists for the parity mode's nn = 64 kernel only
+    constexpr bool CAN_PROF = NN == 64 && SPLIT;
+    const bool prof_on = CAN_PROF && g_prof_buf != nullptr;
+    auto kernel = prof_on ? edge_kernel_tc<NN, SPLIT, CAN_PROF> : edge_kernel_tc<NN, SPLIT, false>;
+    { const int rc_ = device_setup((const void *)kernel, SM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }
     constexpr int TA = 128 / NN;
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int grid = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
     if (!wd) wd = device_watchdog_word();
-    PESTO_CUDA(launch_pdl(edge_kernel_tc<NN, SPLIT>, dim3(grid), dim3(CTA_THREADS), SM_TOTAL, st, (const unsigned char *)tcw, n_atoms,
+    PESTO_CUDA(launch_pdl(kernel, dim3(grid), dim3(CTA_THREADS), SM_TOTAL, st, (const unsigned char *)tcw, n_atoms,
                           ids32, (const float4 *)geom, state_in, nodeT, nodeC, Zout, g_prof_buf, g_prof_tiles, wd));
     return PESTO_OK;
 }

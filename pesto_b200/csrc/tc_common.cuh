@@ -160,6 +160,27 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 
+// The same bounded wait on a barrier given by its 32-bit shared-memory address (computed once per kernel: the generic ->
+// shared conversion costs a handful of instructions per call, and a tile waits a dozen times)
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar_addr, uint32_t parity, int *watchdog, int stage, uint32_t max_spin = 1u << 20) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < max_spin; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return true;
+    }
+    if (watchdog) atomicMax(watchdog, stage);
+    return false;
+}
+
 // ---- bulk async copy global -> shared (TMA engine, no tensor map): completes `bytes` on the mbarrier ---------------
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
