@@ -35,7 +35,12 @@ def pack_batches(sizes, target=TARGET_ATOMS_PER_BATCH, num_nn=64):
         cur.append(i)
         load += int(n)
     if cur:
-        batches.append(cur)
+        # a small tail (< target / 4) rides along with the previous batch: a forward over a few thousand atoms is launch-bound
+        prev_ok = batches and all(int(sizes[j]) >= num_nn for j in batches[-1])
+        if prev_ok and load < target // 4 and all(int(sizes[j]) >= num_nn for j in cur):
+            batches[-1].extend(cur)
+        else:
+            batches.append(cur)
     return batches
 
 
@@ -77,6 +82,12 @@ class _PinnedSlot:
         self.buf = {}
         self.copied = None          # event: the slot's last H2D copies have completed
 
+    def reserve(self, name, numel, dtype):
+        """Size a buffer once for the largest batch of the job (growing it batch by batch costs a pinned allocation each time)."""
+        t = self.buf.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            self.buf[name] = torch.empty(max(int(numel), 1), dtype=dtype).pin_memory()
+
     def put(self, name, arr):
         t = self.buf.get(name)
         if t is None or t.numel() < arr.size or t.dtype != torch.from_numpy(arr[:0]).dtype:
@@ -85,6 +96,35 @@ class _PinnedSlot:
         v = t[:arr.size].view(arr.shape)
         v.numpy()[...] = arr
         return v
+
+
+class _Staging:
+    """Pinned staging buffers and the copy stream of one device, kept for the life of the process: pinned allocations cost
+    milliseconds each, a job of a few dozen structures only tens of milliseconds of GPU time.  (One job per device at a
+    time: predict_structures is a generator that owns these buffers until it is exhausted.)"""
+    _per_device = {}
+
+    def __init__(self, dev):
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.slots = [_PinnedSlot(), _PinnedSlot()]
+        self.zpin = [None, None]
+        self.spin = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        if key not in cls._per_device:
+            cls._per_device[key] = cls(dev)
+        return cls._per_device[key]
+
+    def reserve(self, n_atoms_max):
+        for slot in self.slots:
+            slot.reserve("X", 3 * n_atoms_max, torch.float32)
+            slot.reserve("el", n_atoms_max, torch.uint8)
+            slot.reserve("rid", n_atoms_max, torch.int32)
+        for k in range(2):
+            if self.zpin[k] is None or self.zpin[k].shape[0] < n_atoms_max // 4:
+                self.zpin[k] = torch.empty((max(n_atoms_max // 4, 1024), 5), dtype=torch.float32).pin_memory()
 
 
 def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATOMS_PER_BATCH, num_nn=64):
@@ -97,8 +137,11 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
     dev = torch.device(device)
     sizes = [len(s["xyz"]) for s in structures]
     batches = pack_batches(sizes, target_atoms, num_nn)
-    copy_stream = torch.cuda.Stream(dev)
-    slots = [_PinnedSlot(), _PinnedSlot()]
+    staging = _Staging.get(dev)
+    staging.reserve(max((sum(sizes[i] for i in b) for b in batches), default=0))
+    copy_stream, slots = staging.copy_stream, staging.slots
+    for slot in slots:
+        slot.copied = None
 
     def stage(k):
         slot = slots[k % 2]
@@ -115,7 +158,7 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
         return on_dev, slot.copied, n_at, n_rs
 
     nxt = stage(0) if batches else None
-    zpin, spin = [None, None], [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+    zpin, spin = staging.zpin, staging.spin                     # (zpin is grown below if a batch has more residues than atoms / 4)
 
     def finish(job):            # wait for a batch's logits and status words, hand out per-structure results
         k, b, n_rs, zh, done = job
@@ -137,7 +180,7 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
                 t.record_stream(main)
             ids1 = batch_topology(Xd, n_at, num_nn)
             z = model(Xd, ids1, q0d, ridd, n_res=int(sum(n_rs)))
-            if zpin[k % 2] is None or zpin[k % 2].shape[0] < z.shape[0]:
+            if zpin[k % 2].shape[0] < z.shape[0]:
                 zpin[k % 2] = torch.empty((z.shape[0] * 5 // 4, 5), dtype=torch.float32).pin_memory()
             zh = zpin[k % 2][:z.shape[0]]
             zh.copy_(z, non_blocking=True)

@@ -128,6 +128,7 @@ def test_runner_packing_and_encoding():
     # fewer atoms than neighbours: sink-padded slots read X[-1] of the batch, so such a structure is batched alone
     assert pack_batches([500, 63, 64, 500], 2000) == [[0], [1], [2, 3]]
     assert pack_batches([5, 5, 5], 10, num_nn=4) == [[0, 1], [2]]
+    assert pack_batches([600, 300, 200], 1000) == [[0, 1, 2]]              # a tail below target / 4 rides along
     a = {"xyz": np.zeros((4, 3)), "element": np.array(["C", "N", "Zz", "O"]), "resid": np.array([7, 7, 3, 9])}
     b = {"xyz": np.ones((2, 3)), "element": np.array(["S", "C"]), "resid": np.array([1, 2])}
     X, q0, rid, n_at, n_rs = encode_batch([a, b])
