@@ -122,6 +122,14 @@ int    pesto_state_update_timed(const pesto_model_t *m, int layer, int n_atoms, 
                                 void *node_scratch, int mode, void *stream,
                                 float *ms_node_host, float *ms_edge_host);
 
+/* Measurement aid: the fused edge kernel of `layer` alone, launched reps times back to back on `stream` between two CUDA
+ * events (after one launch of the per-atom kernel that produces the layer's factors from state_in, and one untimed
+ * warm-up launch); *ms_per_launch_host = elapsed / reps.  Tensor-core modes only.  The attention sums land in the Z
+ * region of node_scratch (pesto_node_scratch_bytes); state_in is not modified. */
+int pesto_edge_kernel_timed(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
+                            const float *state_in, void *node_scratch, int mode, int reps, void *stream,
+                            float *ms_per_launch_host);
+
 /* dense one-hot membership M[n_atoms, n_res] (fp32, the reference's 4th forward argument) -> residue
  * column per atom.  flags[0] is set non-zero on device if some row is not one-hot. */
 int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream);

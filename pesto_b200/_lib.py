@@ -33,6 +33,7 @@ SIGNATURES = {
     "pesto_node_scratch_bytes": (_sz, [_i]),
     "pesto_state_update": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pesto_state_update_timed": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pesto_edge_kernel_timed": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pesto_residue_index": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "pesto_pool_scratch_bytes": (_sz, [_i, _i]),
     "pesto_pool_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

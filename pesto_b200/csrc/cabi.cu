@@ -390,6 +390,35 @@ int pesto_state_update_timed(const pesto_model_t *m, int layer, int n_atoms, con
     return rc;
 }
 
+int pesto_edge_kernel_timed(const pesto_model_t *m, int layer, int n_atoms, const int32_t *ids32, const float *geom,
+                            const float *state_in, void *node_scratch, int mode, int reps, void *stream,
+                            float *ms_per_launch_host) {
+    if (!valid_model(m, "pesto_edge_kernel_timed")) return PESTO_ESTATE;
+    if (layer < 0 || layer >= m->n_layers || n_atoms < 1 || !ids32 || !geom || !state_in || !node_scratch || reps < 1 ||
+        !ms_per_launch_host || (mode != PESTO_MODE_F16X3 && mode != PESTO_MODE_F16)) {
+        set_error("pesto_edge_kernel_timed: bad arguments (tensor-core modes only)");
+        return PESTO_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float *ns = (float *)node_scratch;
+    const void *nimg = (const void *)((const unsigned char *)m->layer_tc(layer) + tc_edge_bytes());
+    int rc = launch_node_umma(nullptr, nimg, state_in, nullptr, nullptr, n_atoms, ns, mode, st);      // the layer's per-atom factors
+    if (rc != PESTO_OK) return rc;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) PESTO_CUDA(cudaEventCreate(&ev[i]));
+    rc = launch_edge_tc_layer(m->layer(layer), m->layer_tc(layer), m->nn[layer], n_atoms, ids32, geom, state_in, ns, node_Z(ns, n_atoms), mode, st);
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventRecord(ev[0], st), "cudaEventRecord");
+    for (int r = 0; r < reps && rc == PESTO_OK; ++r)
+        rc = launch_edge_tc_layer(m->layer(layer), m->layer_tc(layer), m->nn[layer], n_atoms, ids32, geom, state_in, ns, node_Z(ns, n_atoms), mode, st);
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventRecord(ev[1], st), "cudaEventRecord");
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventSynchronize(ev[1]), "cudaEventSynchronize");
+    float ms = 0.f;
+    if (rc == PESTO_OK) rc = check_cuda(cudaEventElapsedTime(&ms, ev[0], ev[1]), "cudaEventElapsedTime");
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ev[i]);
+    *ms_per_launch_host = ms / (float)reps;
+    return rc;
+}
+
 int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream) {
     if (!M || !rid || !flags || n_atoms < 1 || n_res < 1) {
         set_error("pesto_residue_index: null pointer or bad sizes");

@@ -36,8 +36,14 @@ resname_to_categ = {rn: c for c, names in categ_to_resnames.items() for rn in na
 
 def onehot(x, v):
     """[len(x), len(v)+1] bool: membership in vocabulary v, last column = not in v (src/data_encoding.py:56-58)."""
-    hit = np.asarray(x).reshape(-1, 1) == np.asarray(v).reshape(1, -1)
-    return np.concatenate([hit, ~hit.any(axis=1, keepdims=True)], axis=1)
+    x, v = np.asarray(x).reshape(-1), np.asarray(v).reshape(-1)
+    order = np.argsort(v, kind="stable")
+    vs = v[order]
+    pos = np.minimum(np.searchsorted(vs, x), len(vs) - 1) if len(vs) else np.zeros(len(x), dtype=np.int64)
+    col = np.where(vs[pos] == x, order[pos], len(v)) if len(vs) else np.full(len(x), len(v))
+    out = np.zeros((len(x), len(v) + 1), dtype=bool)          # one binary search per entry instead of a [N, V] string comparison
+    out[np.arange(len(x)), col] = True
+    return out
 
 
 def encode_structure(structure, device=torch.device("cpu")):

@@ -17,7 +17,7 @@ _RECORD = "{:<6s}{:>5d} {:<4s} {:>3s} {:1s}{:>4d}    {:8.3f}{:8.3f}{:8.3f}{:6.2f
 
 def _chars(buf, n, width):
     """fixed-width NUL-padded character fields -> numpy unicode array"""
-    return np.char.decode(np.frombuffer(buf, dtype=f"S{width}", count=n), "ascii")
+    return np.frombuffer(buf, dtype=f"S{width}", count=n).astype(f"U{width}")      # (C loop; np.char.decode goes through Python per element)
 
 
 def parse_pdb_text(text):
@@ -39,7 +39,10 @@ def parse_pdb_text(text):
                                   bfac.ctypes.data, ctypes.byref(n))
     _lib.check(rc, "pesto_pdb_parse_host")
     n = n.value
-    chains = _chars(chain.raw, n, 1)
+    # '<chain>:<model index>' per atom: format once per distinct (chain, model) pair, not once per atom
+    pair = np.frombuffer(chain.raw, dtype=np.uint8, count=n).astype(np.int64) * (1 << 32) + model[:n].astype(np.int64)
+    upair, inv = np.unique(pair, return_inverse=True)
+    chain_names = np.array([f"{chr(int(u >> 32))}:{int(u & 0xffffffff)}" for u in upair], dtype=str)[inv] if n else np.array([], dtype=str)
     return {
         "xyz": xyz[:n].copy(),
         "name": _chars(name.raw, n, 4),
@@ -47,7 +50,7 @@ def parse_pdb_text(text):
         "resname": _chars(resn.raw, n, 3),
         "resid": resid[:n].copy(),
         "het_flag": _chars(het.raw, n, 1),
-        "chain_name": np.array([f"{c}:{m}" for c, m in zip(chains, model[:n])], dtype=str),
+        "chain_name": chain_names,
         "icode": _chars(icode.raw, n, 1),
         "bfactor": bfac[:n].copy(),          # extension: the reference drops it; the apply path never reads it
     }
