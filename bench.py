@@ -607,7 +607,7 @@ def main():
             "e2e": {"value": total_atoms * args.steps / (ms_e2e * 1e-3), "unit": "atoms/s",
                     "h2d_bytes_per_step": int(Xh.numel() * 4 + elh.numel() + ridh.numel() * 4),
                     "d2h_bytes_per_step": int(zbuf.numel() * 4), "ms_per_step": ms_e2e / args.steps,
-                    "includes": "pinned H2D of X / element index (uint8, one-hot expanded on the device) / residue index, kNN topology (3 launches), forward, D2H of logits",
+                    "includes": "pinned H2D of X / element index (uint8, one-hot expanded on the device) / residue index, kNN topology (4 launches), forward, D2H of logits",
                     "logits_equal_resident_run": same,
                     "runner": {"atoms_per_s": total_atoms / s_runner, "seconds": s_runner, "host_atoms_per_s_per_process": host_atoms_per_s,
                                "includes": "the same shard as structure dictionaries through runner.predict_structures: host encoding, "

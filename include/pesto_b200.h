@@ -68,7 +68,7 @@ const char *pesto_last_error(void);
  *   base = 1: ids are 1-based global row numbers with 0 = sink in unfilled columns
  *             (what collate_batch_features hands to Model.forward).
  * d_out[n_atoms,k] / r_out[n_atoms,k,3] (optional, may be NULL) receive D_topk / R_topk.
- * scratch: at least pesto_knn_scratch_bytes(n_atoms, n_seg) bytes.
+ * scratch: at least pesto_knn_scratch_bytes(n_atoms, n_seg) bytes, 16-byte aligned (chunk bounding boxes + row flags).
  * ------------------------------------------------------------------------------------------- */
 size_t pesto_knn_scratch_bytes(int n_atoms, int n_seg);
 int    pesto_knn(const float *X, int n_atoms, const int32_t *seg_off, int n_seg, int k, int base,

@@ -261,7 +261,7 @@ int pesto_knn(const float *X, int n_atoms, const int32_t *seg_off, int n_seg, in
     }
     return launch_knn(X, n_atoms, seg_off, n_seg, k, base ? 1 : 0, ids_out, d_out, r_out, scratch, (cudaStream_t)stream);
 }
-int pesto_knn_launch_count(void) { return 3; }
+int pesto_knn_launch_count(void) { return 4; }
 
 pesto_model_t *pesto_model_create(int n_layers, const int32_t *nn_per_layer_host, int q0_dim) {
     if (n_layers < 1 || !nn_per_layer_host || q0_dim < 1 || q0_dim > HeadLayout::MAXQ0) {

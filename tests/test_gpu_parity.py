@@ -90,6 +90,29 @@ def test_knn_duplicate_atoms_and_tiny_structures():
         assert torch.equal(torch.nan_to_num(r.cpu()), torch.nan_to_num(orr)), n
 
 
+def test_knn_box_pruning_is_exact_for_any_atom_order():
+    """The chunk bounding boxes only prune: shuffled atoms (every box spans the structure), a chain folded back on itself
+    and a far-away second domain give the oracle's rows bit for bit; structure boundaries fall inside 32-atom chunks."""
+    from pesto_b200.data_encoding import batch_topology, extract_topology
+    X, _, _ = synth_structure(1500, 21)
+    g = torch.Generator().manual_seed(3)
+    shuffled = X[torch.randperm(1500, generator=g)].contiguous()
+    far = torch.cat([X[:700], X[700:] + 500.0]).contiguous()                 # second domain 500 A away: its chunks are skipped
+    folded = torch.cat([X[:750], X[:750].flip(0) + 0.37]).contiguous()       # index-distant atoms are the nearest ones
+    for name, Xn in (("shuffled", shuffled), ("far", far), ("folded", folded)):
+        ids, d, r, _, _ = extract_topology(Xn.cuda(), 64)
+        oi, od, orr = O.extract_topology(Xn, 64)
+        assert torch.equal(ids.cpu(), oi), name
+        assert torch.equal(d.cpu(), od), name
+        assert torch.equal(r.cpu(), orr), name
+    sizes = [333, 70, 1097]                                                    # boundaries inside chunks
+    ids1 = batch_topology(shuffled.cuda(), sizes, 64).cpu()
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    parts = [(shuffled[off[i]:off[i + 1]], O.extract_topology(shuffled[off[i]:off[i + 1]], 64)[0], torch.zeros((n, 1)),
+              torch.zeros(n, dtype=torch.long), 1) for i, n in enumerate(sizes)]
+    assert torch.equal(ids1, O.collate(parts)[1])
+
+
 def test_batch_topology_equals_collate_of_per_structure_knn():
     """One launch over a batch of structures == per-structure topology + collate (index shift, sink padding)."""
     from pesto_b200.data_encoding import batch_topology
