@@ -38,7 +38,7 @@ extern "C" {
 #define PESTO_NK            3   /* key width Nk                                          */
 #define PESTO_MAX_NN       64   /* neighbours kept per atom  (extract_topology(X, 64))    */
 #define PESTO_STATE_STRIDE 128  /* floats per atom record: q[32] | p_x[32] | p_y[32] | p_z[32] */
-#define PESTO_NUM_OUT       5   /* logits per residue        (model/config.py 'dm' N2)    */
+#define PESTO_NUM_OUT       5   /* logits per residue of the shipped i_v4 models (model/config.py 'dm' N2); see pesto_model_num_out */
 
 /* arithmetic modes of the per-edge MLPs (state, softmax and accumulators are always fp32) */
 #define PESTO_MODE_FP32     0   /* FFMA everywhere: parity mode                                     */
@@ -81,12 +81,17 @@ int    pesto_knn(const float *X, int n_atoms, const int32_t *seg_off, int n_seg,
  * ("em.0.weight", "sum.7.su.evm.2.bias", "spl.zdm_vec.0.weight", ...), fp32, row-major HOST
  * memory, shapes as in the checkpoint.  pesto_model_finalize packs them into
  * the device layout the kernels read; the model is immutable afterwards.
+ * The depth of the embedding / decoder heads and the number of logits per residue are read off the
+ * tensors: three Linear layers when "em.2.weight" / "dm.2.weight" are present (i_v3_0, i_v4_*:
+ * model/model.py:9-30), one otherwise (model/save/i_v3_1_2021-05-28_12-40/model.py:9-22); the
+ * length of the last decoder bias (<= 8) is pesto_model_num_out (5 for i_v4_*, 1 for i_v3_1).
  * ------------------------------------------------------------------------------------------- */
 pesto_model_t *pesto_model_create(int n_layers, const int32_t *nn_per_layer_host, int q0_dim);
 int            pesto_model_set_tensor(pesto_model_t *m, const char *key, const float *data_host, int64_t numel);
 int            pesto_model_finalize(pesto_model_t *m);
 void           pesto_model_destroy(pesto_model_t *m);
 int            pesto_model_num_layers(const pesto_model_t *m);
+int            pesto_model_num_out(const pesto_model_t *m);      /* logits per residue; 0 before finalize */
 int            pesto_model_layer_nn(const pesto_model_t *m, int layer);
 
 /* ---------------------------------------------------------------------------------------------
@@ -135,7 +140,7 @@ int pesto_edge_kernel_timed(const pesto_model_t *m, int layer, int n_atoms, cons
 int pesto_residue_index(const float *M, int n_atoms, int n_res, int32_t *rid, int32_t *flags, void *stream);
 
 /* StatePoolLayer + decoder -- src/model_operations.py:197-213, model/model.py:46-50.
- * rid[n_atoms] residue column per atom (any order); z[n_res,5].
+ * rid[n_atoms] residue column per atom (any order); z[n_res, pesto_model_num_out(m)] (5 for the i_v4 models).
  * scratch: pesto_pool_scratch_bytes(n_atoms, n_res) bytes. */
 size_t pesto_pool_scratch_bytes(int n_atoms, int n_res);
 int    pesto_pool_decode(const pesto_model_t *m, const float *state, const int32_t *rid, int n_atoms,

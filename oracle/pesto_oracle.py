@@ -101,7 +101,10 @@ def unpack_geometry(X, ids1):
 
 
 def mlp3(w, prefix, x):
-    """Linear-ELU-Linear-ELU-Linear (src/model_operations.py:35-82)."""
+    """Linear-ELU-Linear-ELU-Linear (src/model_operations.py:35-82); a single Linear when the checkpoint has no
+    `<prefix>.2.weight` (the em / dm heads of model/save/i_v3_1_2021-05-28_12-40/model.py:9-22)."""
+    if prefix + ".2.weight" not in w:
+        return x @ w[prefix + ".0.weight"].T + w[prefix + ".0.bias"]
     h = ELU(x @ w[prefix + ".0.weight"].T + w[prefix + ".0.bias"])
     h = ELU(h @ w[prefix + ".2.weight"].T + w[prefix + ".2.bias"])
     return h @ w[prefix + ".4.weight"].T + w[prefix + ".4.bias"]
@@ -195,7 +198,8 @@ def layer_nn(weights):
 
 
 def forward(weights, X, ids1, q0, rid, n_res, dtype=torch.float32, taps=None, chunk=4096):
-    """Logits z[R,5].  X[N,3], ids1[N,64] 1-based (0 = sink), q0[N,30], rid[N] residue column.
+    """Logits z[R,N2] (5; 1 for i_v3_1).  X[N,3], ids1[N,64] 1-based (0 = sink), q0[N,N0] (30; 123 for the v3 models),
+    rid[N] residue column.
 
     `taps`, if a dict, receives {layer: (q, p)} including the sink row, like forward hooks on
     `model.sum[layer]` of the reference.

@@ -28,6 +28,7 @@ SIGNATURES = {
     "pesto_model_finalize": (_i, [_vp]),
     "pesto_model_destroy": (None, [_vp]),
     "pesto_model_num_layers": (_i, [_vp]),
+    "pesto_model_num_out": (_i, [_vp]),
     "pesto_model_layer_nn": (_i, [_vp, _i]),
     "pesto_prologue": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pesto_node_scratch_bytes": (_sz, [_i]),

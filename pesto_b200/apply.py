@@ -21,21 +21,23 @@ from .structure_io import save_pdb
 
 
 def load_model(model_dir, checkpoint="model_ckpt.pt", mode="f16x3", device="cuda"):
-    """Model(config_model) + load_state_dict of the shipped checkpoint (apply_model.ipynb cells 2-4)."""
+    """Model(config_model) + load_state_dict of the shipped checkpoint (apply_model.ipynb cells 2-4); the depth of the em / dm
+    heads follows the checkpoint (the model.py saved with i_v3_1 has single Linear layers)."""
     from . import compat
     compat.install()          # the reference's config.py imports `src.data_encoding` at module level
     spec = importlib.util.spec_from_file_location("pesto_reference_config", os.path.join(model_dir, "config.py"))
     cfg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(cfg)
-    model = Model(cfg.config_model, mode=mode)
-    model.load_state_dict(torch.load(os.path.join(model_dir, checkpoint), map_location="cpu"))
+    model = Model.for_state_dict(cfg.config_model, torch.load(os.path.join(model_dir, checkpoint), map_location="cpu"), mode=mode)
     return model.eval().to(device)
 
 
 def predict_structure(model, structure, device="cuda"):
-    """Per-residue probabilities p[n_res, 5] of one concatenated structure (apply_model.ipynb cell 6, lines 144-158)."""
+    """Per-residue probabilities p[n_res, N2] of one concatenated structure (apply_model.ipynb cell 6, lines 144-158)."""
     X, M = encode_structure(structure)
-    q = encode_features(structure)[0]
+    feats = encode_features(structure)
+    # v4 models: element one-hot; v3 models: element | residue name | atom name (model/save/i_v3_*/src/data_encoding.py:105-108)
+    q = feats[0] if model.config["em"]["N0"] == feats[0].shape[1] else torch.cat(feats, dim=1)
     with torch.no_grad():
         X = X.to(device)
         ids_topk = extract_topology(X, 64)[0]

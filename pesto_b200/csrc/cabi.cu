@@ -71,6 +71,7 @@ using namespace pesto;
 struct pesto_model {
     int n_layers = 0;
     int q0_dim = 0;
+    int em_layers = 3, dm_layers = 3, n_out = PESTO_NUM_OUT;   // found from the tensors at finalize
     std::vector<int> nn;
     std::map<std::string, std::vector<float>> tensors;
     float *d_blob = nullptr;       // [n_layers * LayerLayout::SIZE | HeadLayout::SIZE]
@@ -172,15 +173,34 @@ void pack_layer(Packer &pk, int l, float *dst) {
     pk.transposed(dst + L::O_P, 32, p + "ppm.0.weight", 32, 64);
 }
 
+// The depth of em / dm and the number of logits are read off the checkpoint: `em.2.weight` / `dm.2.weight` exist only in
+// the three-layer heads (model/save/i_v3_1*/model.py:9-13,20-22 has single Linear layers), the last dm bias has N2 entries.
+bool head_architecture(pesto_model *m) {
+    m->em_layers = m->tensors.count("em.2.weight") ? 3 : 1;
+    m->dm_layers = m->tensors.count("dm.2.weight") ? 3 : 1;
+    auto it = m->tensors.find(m->dm_layers == 3 ? "dm.4.bias" : "dm.0.bias");
+    if (it == m->tensors.end() || it->second.empty() || it->second.size() > 8) {
+        set_error("model_finalize: the decoder's output bias (dm.%d.bias) is missing or has more than 8 entries", m->dm_layers == 3 ? 4 : 0);
+        return false;
+    }
+    m->n_out = (int)it->second.size();
+    return true;
+}
+
 void pack_head(Packer &pk, float *dst) {
     using H = HeadLayout;
-    const int q0 = pk.m->q0_dim;
+    const int q0 = pk.m->q0_dim, n_out = pk.m->n_out;
+    dst[H::META_EM_LAYERS] = (float)pk.m->em_layers;
+    dst[H::META_DM_LAYERS] = (float)pk.m->dm_layers;
+    dst[H::META_NUM_OUT] = (float)n_out;
     pk.transposed(dst + H::EM_W1, 32, "em.0.weight", 32, q0);
     pk.vec(dst + H::EM_B1, "em.0.bias", 32);
-    pk.transposed(dst + H::EM_W2, 32, "em.2.weight", 32, 32);
-    pk.vec(dst + H::EM_B2, "em.2.bias", 32);
-    pk.transposed(dst + H::EM_W3, 32, "em.4.weight", 32, 32);
-    pk.vec(dst + H::EM_B3, "em.4.bias", 32);
+    if (pk.m->em_layers == 3) {
+        pk.transposed(dst + H::EM_W2, 32, "em.2.weight", 32, 32);
+        pk.vec(dst + H::EM_B2, "em.2.bias", 32);
+        pk.transposed(dst + H::EM_W3, 32, "em.4.weight", 32, 32);
+        pk.vec(dst + H::EM_B3, "em.4.bias", 32);
+    }
     pk.transposed(dst + H::SAM_W1, 32, "spl.sam.0.weight", 32, 64);
     pk.vec(dst + H::SAM_B1, "spl.sam.0.bias", 32);
     pk.transposed(dst + H::SAM_W2, 32, "spl.sam.2.weight", 32, 32);
@@ -194,12 +214,17 @@ void pack_head(Packer &pk, float *dst) {
     pk.transposed(dst + H::ZDM_W3, 32, "spl.zdm.4.weight", 32, 32);
     pk.vec(dst + H::ZDM_B3, "spl.zdm.4.bias", 32);
     pk.transposed(dst + H::ZDV_W, 32, "spl.zdm_vec.0.weight", 32, 128);
-    pk.transposed(dst + H::DM_W1, 32, "dm.0.weight", 32, 64);
-    pk.vec(dst + H::DM_B1, "dm.0.bias", 32);
-    pk.transposed(dst + H::DM_W2, 32, "dm.2.weight", 32, 32);
-    pk.vec(dst + H::DM_B2, "dm.2.bias", 32);
-    pk.transposed(dst + H::DM_W3, 8, "dm.4.weight", PESTO_NUM_OUT, 32);
-    pk.vec(dst + H::DM_B3, "dm.4.bias", PESTO_NUM_OUT);
+    if (pk.m->dm_layers == 3) {
+        pk.transposed(dst + H::DM_W1, 32, "dm.0.weight", 32, 64);
+        pk.vec(dst + H::DM_B1, "dm.0.bias", 32);
+        pk.transposed(dst + H::DM_W2, 32, "dm.2.weight", 32, 32);
+        pk.vec(dst + H::DM_B2, "dm.2.bias", 32);
+        pk.transposed(dst + H::DM_W3, 8, "dm.4.weight", n_out, 32);
+        pk.vec(dst + H::DM_B3, "dm.4.bias", n_out);
+    } else {
+        pk.transposed(dst + H::DM_W1, 8, "dm.0.weight", n_out, 64);
+        pk.vec(dst + H::DM_B1, "dm.0.bias", n_out);
+    }
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -301,6 +326,7 @@ int pesto_model_finalize(pesto_model_t *m) {
         return PESTO_EINVAL;
     }
     if (m->finalized) return PESTO_OK;
+    if (!head_architecture(m)) return PESTO_ESTATE;
     const size_t n_float = (size_t)m->n_layers * LayerLayout::SIZE + HeadLayout::SIZE;
     std::vector<float> blob(n_float, 0.f);
     Packer pk{m};
@@ -330,6 +356,7 @@ void pesto_model_destroy(pesto_model_t *m) {
 }
 
 int pesto_model_num_layers(const pesto_model_t *m) { return m ? m->n_layers : 0; }
+int pesto_model_num_out(const pesto_model_t *m) { return (m && m->finalized) ? m->n_out : 0; }
 int pesto_model_layer_nn(const pesto_model_t *m, int layer) {
     return (m && layer >= 0 && layer < m->n_layers) ? m->nn[layer] : 0;
 }

@@ -87,13 +87,18 @@ struct HeadLayout {
     static constexpr int ZDM_W3 = ZDM_B2 + 32;
     static constexpr int ZDM_B3 = ZDM_W3 + 32 * 32;
     static constexpr int ZDV_W  = ZDM_B3 + 32;        // spl.zdm_vec.0^T [128][32]
-    static constexpr int DM_W1  = ZDV_W + 128 * 32;   // dm.0^T [64][32]
+    static constexpr int DM_W1  = ZDV_W + 128 * 32;   // dm.0^T [64][32]  (one-layer decoder: dm.0^T [64][8], bias in DM_B1[0..8))
     static constexpr int DM_B1  = DM_W1 + 64 * 32;
     static constexpr int DM_W2  = DM_B1 + 32;
     static constexpr int DM_B2  = DM_W2 + 32 * 32;
     static constexpr int DM_W3  = DM_B2 + 32;         // dm.4^T [32][8] (5 used)
     static constexpr int DM_B3  = DM_W3 + 32 * 8;     // [8]
-    static constexpr int SIZE   = DM_B3 + 8;
+    // architecture of the two heads (model/save/i_v3_1*/model.py has one Linear where the other checkpoints have
+    // Linear-ELU-Linear-ELU-Linear), read by the kernels as warp-uniform values
+    static constexpr int META_EM_LAYERS = DM_B3 + 8;  // 1.0f or 3.0f
+    static constexpr int META_DM_LAYERS = META_EM_LAYERS + 1;
+    static constexpr int META_NUM_OUT   = META_EM_LAYERS + 2;   // logits per residue, 1..8
+    static constexpr int SIZE   = META_EM_LAYERS + 8;
 };
 
 // node-kernel outputs

@@ -153,7 +153,8 @@ residue_kernel(const float *__restrict__ hw, const float *__restrict__ state, co
     // raises from them wherever it synchronises anyway)
     if (flags[1] || (poison && (poison[0] || poison[1] || poison[2]))) {
         if (flags[1] && poison && r == 0 && lane == 0) poison[3] = 1;      // residue index out of range -> status word 4
-        if (lane < PESTO_NUM_OUT) z[(size_t)r * PESTO_NUM_OUT + lane] = __int_as_float(0x7fc00000);
+        const int n_out = (int)hw[H::META_NUM_OUT];
+        if (lane < n_out) z[(size_t)r * n_out + lane] = __int_as_float(0x7fc00000);
         return;
     }
     const bool unsorted = flags[0] != 0;
@@ -223,6 +224,17 @@ residue_kernel(const float *__restrict__ hw, const float *__restrict__ state, co
     for (int k = 0; k < 32; ++k) qr = fmaf(__shfl_sync(FULL, y2, k), __ldg(hw + H::ZDM_W3 + k * 32 + lane), qr);
     const float prn = sqrtf(pr0 * pr0 + pr1 * pr1 + pr2 * pr2);
     // decoder dm([qr, |pr|])
+    const int n_out = (int)hw[H::META_NUM_OUT];
+    if (hw[H::META_DM_LAYERS] < 2.f) {                          // one Linear (model/save/i_v3_1*/model.py:20-22)
+        float o = hw[H::DM_B1 + (lane & 7)];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            o = fmaf(__shfl_sync(FULL, qr, k), __ldg(hw + H::DM_W1 + k * 8 + (lane & 7)), o);
+            o = fmaf(__shfl_sync(FULL, prn, k), __ldg(hw + H::DM_W1 + (32 + k) * 8 + (lane & 7)), o);
+        }
+        if (lane < n_out) z[(size_t)r * n_out + lane] = o;
+        return;
+    }
     float d1 = hw[H::DM_B1 + lane];
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
@@ -237,7 +249,7 @@ residue_kernel(const float *__restrict__ hw, const float *__restrict__ state, co
     float o = hw[H::DM_B3 + (lane & 7)];
 #pragma unroll
     for (int k = 0; k < 32; ++k) o = fmaf(__shfl_sync(FULL, d2, k), __ldg(hw + H::DM_W3 + k * 8 + (lane & 7)), o);
-    if (lane < PESTO_NUM_OUT) z[(size_t)r * PESTO_NUM_OUT + lane] = o;
+    if (lane < n_out) z[(size_t)r * n_out + lane] = o;
 }
 
 struct PoolScratch {

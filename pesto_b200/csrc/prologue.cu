@@ -7,7 +7,8 @@ namespace pesto {
 
 namespace {
 
-// one warp per atom; lane = output unit of the 3-layer embedding MLP (Linear-ELU-Linear-ELU-Linear)
+// one warp per atom; lane = output unit of the embedding MLP (Linear-ELU-Linear-ELU-Linear, or the single Linear of
+// model/save/i_v3_1*/model.py:9-11)
 __global__ void __launch_bounds__(256)
 embed_kernel(const float *__restrict__ hw, int q0_dim, const float *__restrict__ q0, int n_atoms,
              float *__restrict__ state) {
@@ -22,6 +23,11 @@ embed_kernel(const float *__restrict__ hw, int q0_dim, const float *__restrict__
     const float *x = q0 + (size_t)(row - 1) * q0_dim;
     float h = hw[HeadLayout::EM_B1 + lane];
     for (int k = 0; k < q0_dim; ++k) h = fmaf(__ldg(x + k), hw[HeadLayout::EM_W1 + k * 32 + lane], h);
+    if (hw[HeadLayout::META_EM_LAYERS] < 2.f) {                 // one-layer embedding
+        out[lane] = h;
+        out[32 + lane] = out[64 + lane] = out[96 + lane] = 0.f;
+        return;
+    }
     h = elu(h);
     float g = hw[HeadLayout::EM_B2 + lane];
 #pragma unroll

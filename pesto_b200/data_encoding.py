@@ -34,15 +34,23 @@ categ_to_resnames = {
 resname_to_categ = {rn: c for c, names in categ_to_resnames.items() for rn in names}
 
 
-def onehot(x, v):
-    """[len(x), len(v)+1] bool: membership in vocabulary v, last column = not in v (src/data_encoding.py:56-58)."""
+def onehot_index(x, v):
+    """Column of every entry of x in `onehot(x, v)`: its position in vocabulary v, or len(v) ("not in v", the last column) --
+    one binary search per entry instead of a [N, V] string comparison."""
     x, v = np.asarray(x).reshape(-1), np.asarray(v).reshape(-1)
+    if not len(v):
+        return np.zeros(len(x), dtype=np.int64)
     order = np.argsort(v, kind="stable")
     vs = v[order]
-    pos = np.minimum(np.searchsorted(vs, x), len(vs) - 1) if len(vs) else np.zeros(len(x), dtype=np.int64)
-    col = np.where(vs[pos] == x, order[pos], len(v)) if len(vs) else np.full(len(x), len(v))
-    out = np.zeros((len(x), len(v) + 1), dtype=bool)          # one binary search per entry instead of a [N, V] string comparison
-    out[np.arange(len(x)), col] = True
+    pos = np.minimum(np.searchsorted(vs, x), len(vs) - 1)
+    return np.where(vs[pos] == x, order[pos], len(v))
+
+
+def onehot(x, v):
+    """[len(x), len(v)+1] bool: membership in vocabulary v, last column = not in v (src/data_encoding.py:56-58)."""
+    col = onehot_index(x, v)
+    out = np.zeros((len(col), len(v) + 1), dtype=bool)
+    out[np.arange(len(col)), col] = True
     return out
 
 

@@ -16,7 +16,7 @@ def _residue_index(M):
 
 
 def predict_trajectory(model, X_traj, ids_topk, q, M, frames=None, frames_per_batch=None, device="cuda"):
-    """Logits z[len(frames), R, 5] for the frames of X_traj [N, T, 3] (atoms, frames, xyz -- the notebook's layout).
+    """Logits z[len(frames), R, N2] (N2 = 5 for the i_v4 models) for the frames of X_traj [N, T, 3] (atoms, frames, xyz -- the notebook's layout).
 
     ids_topk [N, 64] int64 is what collate_batch_features returns (1-based, 0 = sink) and is reused for every
     frame; q [N, 30]; M dense [N, R] or a residue index [N].  `frames`: iterable of frame numbers (default: all).
@@ -36,7 +36,8 @@ def predict_trajectory(model, X_traj, ids_topk, q, M, frames=None, frames_per_ba
     ids_b = torch.where(ids.unsqueeze(0) > 0, ids.unsqueeze(0) + shift, torch.zeros_like(ids).unsqueeze(0)).reshape(per * n_atoms, -1)
     rid_b = (rid.unsqueeze(0) + (torch.arange(per, device=dev) * n_res).view(per, 1)).reshape(-1).to(torch.int32)
     q_b = qd.repeat(per, 1)
-    out = torch.empty((len(frames), n_res, 5), dtype=torch.float32, device=dev)
+    n_out = getattr(model, "num_out", 5)
+    out = torch.empty((len(frames), n_res, n_out), dtype=torch.float32, device=dev)
     Xd = X_traj if X_traj.is_cuda else None
     with torch.no_grad():
         for b0 in range(0, len(frames), per):
@@ -46,7 +47,7 @@ def predict_trajectory(model, X_traj, ids_topk, q, M, frames=None, frames_per_ba
             Xb = (Xd if Xd is not None else X_traj).index_select(1, idx).permute(1, 0, 2).reshape(f * n_atoms, 3)
             Xb = Xb.to(dev, torch.float32, non_blocking=True).contiguous()
             z = model(Xb, ids_b[:f * n_atoms], q_b[:f * n_atoms], rid_b[:f * n_atoms], n_res=f * n_res)
-            out[b0:b0 + f] = z.view(f, n_res, 5)
+            out[b0:b0 + f] = z.view(f, n_res, n_out)
             if b0 == 0 or b0 + per >= len(frames):
                 model.raise_if_failed(dev)     # input flags show on the first batch (topology and membership are shared by all frames)
     return out

@@ -58,9 +58,12 @@ class StatePoolLayer(torch.nn.Module):
 
 
 class Model(torch.nn.Module):
-    """Drop-in for the reference `Model` (inference only).
+    """Drop-in for the reference `Model` (inference only): model/model.py:6-52 and the per-checkpoint copies under
+    model/save/*/model.py.  Those copies differ in one respect only: i_v3_1 (model/save/i_v3_1_2021-05-28_12-40/model.py:9-22)
+    has a single Linear as embedding and as decoder where the other checkpoints have Linear-ELU-Linear-ELU-Linear; pass
+    `em_layers=1, dm_layers=1` for it (or build the model with `Model.for_state_dict`, which reads the depth off the keys).
 
-    forward(X, ids_topk, q0, M) -> z[R, 5] logits on the input device.
+    forward(X, ids_topk, q0, M) -> z[R, N2] logits on the input device (N2 = config['dm']['N2']: 5 for i_v4_*, 1 for i_v3_1).
       X         [N, 3] float32 coordinates
       ids_topk  [N, K<=64] int64, 1-based, 0 = sink   (what collate_batch_features returns)
       q0        [N, N0] float32 features
@@ -71,23 +74,39 @@ class Model(torch.nn.Module):
     'bf16x3' / 'bf16' are accepted as former names of the two tensor-core modes.
     """
 
-    def __init__(self, config, mode="f16x3"):
+    def __init__(self, config, mode="f16x3", em_layers=3, dm_layers=3):
         super().__init__()
         for lp in config["sum"]:
             if (lp["Ns"], lp["Nh"], lp["Nk"]) != (32, 2, 3) or lp["nn"] not in (8, 16, 32, 64):
                 raise ValueError(f"unsupported layer parameters {lp}: kernels are built for Ns=32, Nh=2, Nk=3, nn in 8/16/32/64")
         if config["em"]["N1"] != 32 or config["spl"] != {"N0": 32, "N1": 32, "Nh": 4} or \
-                (config["dm"]["N0"], config["dm"]["N1"], config["dm"]["N2"]) != (32, 32, 5):
+                (config["dm"]["N0"], config["dm"]["N1"]) != (32, 32) or not 1 <= config["dm"]["N2"] <= 8 or \
+                not 1 <= config["em"]["N0"] <= 128 or em_layers not in (1, 3) or dm_layers not in (1, 3):
             raise ValueError("unsupported em/spl/dm configuration for the CUDA kernels")
         self.config = config
         self.mode = mode
-        self.em = _mlp(config["em"]["N0"], config["em"]["N1"], config["em"]["N1"])
+        self.num_out = int(config["dm"]["N2"])
+        if em_layers == 3:
+            self.em = _mlp(config["em"]["N0"], config["em"]["N1"], config["em"]["N1"])
+        else:
+            self.em = torch.nn.Sequential(torch.nn.Linear(config["em"]["N0"], config["em"]["N1"]))
         self.sum = torch.nn.Sequential(*[StateUpdateLayer(lp) for lp in config["sum"]])
         self.spl = StatePoolLayer(config["spl"]["N0"], config["spl"]["N1"], config["spl"]["Nh"])
-        self.dm = _mlp(2 * config["dm"]["N0"], config["dm"]["N1"], config["dm"]["N2"])
+        if dm_layers == 3:
+            self.dm = _mlp(2 * config["dm"]["N0"], config["dm"]["N1"], config["dm"]["N2"])
+        else:
+            self.dm = torch.nn.Sequential(torch.nn.Linear(2 * config["dm"]["N0"], config["dm"]["N2"]))
         self._handles = {}        # device index -> C model handle
         self._workspaces = {}     # device index -> uint8 tensor
         self._last = {}           # device index -> (aligned workspace pointer, n_atoms, n_res) of the last forward
+
+    @classmethod
+    def for_state_dict(cls, config, state_dict, mode="f16x3"):
+        """Model with the head depths the checkpoint has (`em.2.weight` / `dm.2.weight` present -> three layers), loaded."""
+        model = cls(config, mode=mode, em_layers=3 if "em.2.weight" in state_dict else 1,
+                    dm_layers=3 if "dm.2.weight" in state_dict else 1)
+        model.load_state_dict(state_dict)
+        return model
 
     # ---- packed-weight handle management ------------------------------------------------------------------
     def _invalidate(self):
@@ -131,6 +150,8 @@ class Model(torch.nn.Module):
                 _lib.check(lib.pesto_model_set_tensor(h, key.encode(), a.ctypes.data, a.size), f"set_tensor({key})")
             with torch.cuda.device(dev_index):
                 _lib.check(lib.pesto_model_finalize(h), "pesto_model_finalize")
+            if lib.pesto_model_num_out(h) != self.num_out:
+                raise _lib.PestoError(f"the decoder packs {lib.pesto_model_num_out(h)} logits per residue, the configuration says {self.num_out}")
         except Exception:
             lib.pesto_model_destroy(h)
             raise
@@ -181,7 +202,7 @@ class Model(torch.nn.Module):
             h = self._handle(dev.index)
             nbytes = lib.pesto_forward_workspace_bytes(n_atoms, n_res)
             ws = self._workspace(dev, nbytes)
-            z = torch.empty((n_res, 5), dtype=torch.float32, device=dev)
+            z = torch.empty((n_res, self.num_out), dtype=torch.float32, device=dev)
             base = ws.data_ptr()
             aligned = (base + 255) // 256 * 256
             stream = torch.cuda.current_stream(dev).cuda_stream

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .data_encoding import batch_topology, onehot, std_elements
+from .data_encoding import batch_topology, onehot, onehot_index, std_elements, std_names, std_resnames
 
 TARGET_ATOMS_PER_BATCH = 131072
 
@@ -44,28 +44,48 @@ def pack_batches(sizes, target=TARGET_ATOMS_PER_BATCH, num_nn=64):
     return batches
 
 
-_EL_SORT = np.argsort(std_elements)
-_EL_SORTED = std_elements[_EL_SORT]
+# feature blocks of q0 (src/data_encoding.py:78-84): the v4 models take the element one-hot (30 columns), the v3 models the
+# concatenation element | residue name | atom name (30 + 29 + 64 = 123 columns, model/save/i_v3_*/src/data_encoding.py:105-108)
+FEATURE_BLOCKS = {30: (("element", std_elements),),
+                  123: (("element", std_elements), ("resname", std_resnames), ("name", std_names))}
 
 
 def element_index(elements):
     """Column of every atom in the element one-hot of src/data_encoding.py:56-58,78-84: position in std_elements, or
-    len(std_elements) (= "unknown", the last column) -- as uint8, via one binary search instead of a [N, 29] comparison."""
-    el = np.asarray(elements)
-    pos = np.minimum(np.searchsorted(_EL_SORTED, el), len(_EL_SORTED) - 1)
-    return np.where(_EL_SORTED[pos] == el, _EL_SORT[pos], len(std_elements)).astype(np.uint8)
+    len(std_elements) (= "unknown", the last column) -- as uint8."""
+    return onehot_index(elements, std_elements).astype(np.uint8)
 
 
-def encode_batch(structures, as_index=False):
-    """Host side of one batch: X [N,3] f32, q0 [N,30] f32 (element one-hot, src/data_encoding.py:78-84; with as_index
-    the uint8 column index instead, expanded on the device), residue index [N] int32 (position of the atom's resid among
-    the structure's sorted unique resids, src/data_encoding.py:73, plus the batch's residue offset), per-structure atom
-    and residue counts."""
+def feature_index(structure, n_features=30):
+    """uint8 [N, number of one-hot blocks]: the hot column of each block of q0 (one byte per block crosses PCIe instead of
+    n_features floats; `expand_features` rebuilds q0 on the device)."""
+    if n_features not in FEATURE_BLOCKS:
+        raise ValueError(f"no feature encoding with {n_features} columns (known: {sorted(FEATURE_BLOCKS)})")
+    return np.stack([onehot_index(structure[key], vocab) for key, vocab in FEATURE_BLOCKS[n_features]], axis=1).astype(np.uint8)
+
+
+def expand_features(index, n_features=30):
+    """q0 [N, n_features] float32 on the device of `index` (uint8 [N, blocks] from feature_index)."""
+    blocks = FEATURE_BLOCKS[n_features]
+    if index.dim() == 1:
+        index = index.unsqueeze(1)
+    hot = [torch.nn.functional.one_hot(index[:, b].long(), len(vocab) + 1) for b, (_, vocab) in enumerate(blocks)]
+    return (hot[0] if len(hot) == 1 else torch.cat(hot, dim=1)).to(torch.float32)
+
+
+def encode_batch(structures, as_index=False, n_features=30):
+    """Host side of one batch: X [N,3] f32, q0 [N,n_features] f32 (one-hot blocks, src/data_encoding.py:78-84; with
+    as_index the uint8 hot columns instead, expanded on the device), residue index [N] int32 (position of the atom's
+    resid among the structure's sorted unique resids, src/data_encoding.py:73, plus the batch's residue offset),
+    per-structure atom and residue counts."""
     X = np.concatenate([np.asarray(s["xyz"], dtype=np.float32) for s in structures], axis=0)
     if as_index:
-        q0 = np.concatenate([element_index(s["element"]) for s in structures], axis=0)
+        q0 = np.concatenate([feature_index(s, n_features) for s in structures], axis=0)
+        if q0.shape[1] == 1:
+            q0 = q0[:, 0]                                       # one block: a flat index vector
     else:
-        q0 = np.concatenate([onehot(s["element"], std_elements) for s in structures], axis=0).astype(np.float32)
+        q0 = np.concatenate([np.concatenate([onehot(s[key], vocab) for key, vocab in FEATURE_BLOCKS[n_features]], axis=1)
+                             for s in structures], axis=0).astype(np.float32)
     rids, n_res, r0 = [], [], 0
     for s in structures:
         u, inv = np.unique(np.asarray(s["resid"]), return_inverse=True)
@@ -117,18 +137,19 @@ class _Staging:
             cls._per_device[key] = cls(dev)
         return cls._per_device[key]
 
-    def reserve(self, n_atoms_max):
+    def reserve(self, n_atoms_max, n_blocks=1, n_out=5):
         for slot in self.slots:
             slot.reserve("X", 3 * n_atoms_max, torch.float32)
-            slot.reserve("el", n_atoms_max, torch.uint8)
+            slot.reserve("el", n_blocks * n_atoms_max, torch.uint8)
             slot.reserve("rid", n_atoms_max, torch.int32)
         for k in range(2):
-            if self.zpin[k] is None or self.zpin[k].shape[0] < n_atoms_max // 4:
-                self.zpin[k] = torch.empty((max(n_atoms_max // 4, 1024), 5), dtype=torch.float32).pin_memory()
+            if self.zpin[k] is None or self.zpin[k].shape[0] < n_atoms_max // 4 or self.zpin[k].shape[1] != n_out:
+                self.zpin[k] = torch.empty((max(n_atoms_max // 4, 1024), n_out), dtype=torch.float32).pin_memory()
 
 
 def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATOMS_PER_BATCH, num_nn=64):
-    """Yield (index, z[n_res, 5] float32 on the host) for every structure dictionary (keys xyz, element, resid), in order.
+    """Yield (index, z[n_res, N2] float32 on the host) for every structure dictionary (keys xyz, element, resid -- and
+    resname, name for the 123-feature v3 models), in order.
 
     Pipeline per batch k: (1) its kNN + forward + D2H of logits and status words are enqueued, (2) the host encodes batch
     k+1 and enqueues its pinned H2D copies on a copy stream while the GPU works, (3) the host collects batch k-1's results
@@ -137,8 +158,10 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
     dev = torch.device(device)
     sizes = [len(s["xyz"]) for s in structures]
     batches = pack_batches(sizes, target_atoms, num_nn)
+    n_features = int(model.config["em"]["N0"])
+    n_out = int(getattr(model, "num_out", 5))
     staging = _Staging.get(dev)
-    staging.reserve(max((sum(sizes[i] for i in b) for b in batches), default=0))
+    staging.reserve(max((sum(sizes[i] for i in b) for b in batches), default=0), len(FEATURE_BLOCKS[n_features]), n_out)
     copy_stream, slots = staging.copy_stream, staging.slots
     for slot in slots:
         slot.copied = None
@@ -147,12 +170,12 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
         slot = slots[k % 2]
         if slot.copied is not None:
             slot.copied.synchronize()                       # the buffers' previous copies are long done
-        X, el, rid, n_at, n_rs = encode_batch([structures[i] for i in batches[k]], as_index=True)
+        X, el, rid, n_at, n_rs = encode_batch([structures[i] for i in batches[k]], as_index=True, n_features=n_features)
         host = [slot.put(n, a) for n, a in (("X", X), ("el", el), ("rid", rid))]
         with torch.cuda.stream(copy_stream):
             on_dev = [t.to(dev, non_blocking=True) for t in host]
-            # one byte per atom crosses PCIe; the [N, 30] one-hot Model.forward takes is expanded on the device
-            on_dev[1] = torch.nn.functional.one_hot(on_dev[1].long(), len(std_elements) + 1).to(torch.float32)
+            # one byte per atom and one-hot block crosses PCIe; the [N, N0] one-hots Model.forward takes are expanded on the device
+            on_dev[1] = expand_features(on_dev[1], n_features)
             slot.copied = torch.cuda.Event()
             slot.copied.record(copy_stream)
         return on_dev, slot.copied, n_at, n_rs
@@ -181,7 +204,7 @@ def predict_structures(model, structures, device="cuda", target_atoms=TARGET_ATO
             ids1 = batch_topology(Xd, n_at, num_nn)
             z = model(Xd, ids1, q0d, ridd, n_res=int(sum(n_rs)))
             if zpin[k % 2].shape[0] < z.shape[0]:
-                zpin[k % 2] = torch.empty((z.shape[0] * 5 // 4, 5), dtype=torch.float32).pin_memory()
+                zpin[k % 2] = torch.empty((z.shape[0] * 5 // 4, n_out), dtype=torch.float32).pin_memory()
             zh = zpin[k % 2][:z.shape[0]]
             zh.copy_(z, non_blocking=True)
             spin[k % 2].copy_(model.status_words(dev), non_blocking=True)

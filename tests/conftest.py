@@ -79,9 +79,8 @@ def cuda_models():
 
     def get(tag, mode="fp32"):
         if (tag, mode) not in cache:
-            m = Model(load_config(tag), mode=mode)
             sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
-            m.load_state_dict(sd)
+            m = Model.for_state_dict(load_config(tag), sd, mode=mode)        # head depths read off the checkpoint (i_v3_1: one Linear)
             cache[(tag, mode)] = m.eval().to("cuda")
         return cache[(tag, mode)]
     return get

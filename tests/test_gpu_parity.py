@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, BOTH_MODES, load_case, load_weights, case_tensors
+from conftest import GOLDEN, BOTH_MODES, load_case, load_config, load_weights, case_tensors
 from oracle import pesto_oracle as O
 from oracle import scoring
 from pesto_b200.synth import synth_structure, one_hot_features, dense_membership, BASE_SEED
@@ -528,3 +528,69 @@ def test_config3_batch_of_8192_atom_structures(cuda_models, mode):
         if s == 0:          # 16 layers x 8192 atoms: ~20 s of CPU oracle
             zo = O.forward(load_weights("i_v4_0"), Xs[0], ids1.cpu(), one_hot_features(els[0]), rids[0], n // 8)
             assert (zs.cpu() - zo).abs().max().item() <= (FP32_EXPECTED if mode == "fp32" else 3e-4)
+
+
+# ------------------------------------------------------------------------------------------------- v3 checkpoints
+def _v3_inputs():
+    from pesto_b200.runner import expand_features
+    c = load_case("v3_1gpw_A")
+    X, rid, n_res = torch.from_numpy(c["X"]), torch.from_numpy(c["rid"].astype(np.int64)), int(c["n_res"])
+    q0 = expand_features(torch.from_numpy(c["feat"]), 123)
+    ids1 = O.collate([(X, torch.from_numpy(c["ids0"]).long(), q0, rid, n_res)])[1]
+    return c, X, ids1, q0, rid, n_res
+
+
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_v3_0_checkpoint_matches_reference(cuda_models, mode):
+    """i_v3_0: 123 input features, 16 layers (model/save/i_v3_0_2021-05-27_14-27)."""
+    c, X, ids1, q0, rid, n_res = _v3_inputs()
+    z = cuda_models("i_v3_0", mode)(X.cuda(), ids1.cuda(), q0.cuda(), rid.int().cuda(), n_res=n_res).cpu()
+    assert z.shape == (n_res, 5)
+    assert (z - torch.from_numpy(c["z_i_v3_0"])).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("mode", BOTH_MODES)
+def test_single_linear_heads_match_oracle(mode):
+    """The one-Linear em / dm heads and the single logit of i_v3_1 (model/save/i_v3_1_2021-05-28_12-40/model.py:9-22) on a
+    well-conditioned state: i_v3_1's heads around i_v3_0's layers and pooling (the oracle's fp32 and fp64 runs of this
+    hybrid agree to 9e-7; the real i_v3_1 layers are ill-conditioned, see the next test)."""
+    from pesto_b200.model import Model
+    c, X, ids1, q0, rid, n_res = _v3_inputs()
+    w0, w1 = load_weights("i_v3_0"), load_weights("i_v3_1")
+    hybrid = {k: v for k, v in w0.items() if k.startswith(("sum.", "spl."))}
+    hybrid.update({k: v for k, v in w1.items() if k.startswith(("em.", "dm."))})
+    model = Model.for_state_dict(load_config("i_v3_1"), {k: torch.from_numpy(v) for k, v in hybrid.items()}, mode=mode).cuda()
+    z = model(X.cuda(), ids1.cuda(), q0.cuda(), rid.int().cuda(), n_res=n_res).cpu()
+    zo = O.forward(hybrid, X, ids1, q0, rid, n_res)
+    assert z.shape == zo.shape == (n_res, 1)
+    assert (z - zo).abs().max().item() < 1e-3
+
+
+def test_v3_1_checkpoint_runs_in_fp32_and_is_refused_on_the_fp16_planes(cuda_models):
+    """The shipped i_v3_1 state grows to ~4e5 (tests/test_oracle_golden.py): the fp32 mode reproduces the reference on the
+    median residue (the logits are ill-conditioned beyond that: fp32 vs fp64 of the reference's own arithmetic differ by
+    up to 8.6), the tensor-core mode reports the state leaving the fp16 operand range instead of returning numbers."""
+    from pesto_b200 import _lib
+    c, X, ids1, q0, rid, n_res = _v3_inputs()
+    args = (X.cuda(), ids1.cuda(), q0.cuda(), rid.int().cuda())
+    z = cuda_models("i_v3_1", "fp32")(*args, n_res=n_res).cpu()
+    ref = torch.from_numpy(c["z_i_v3_1"])
+    assert z.shape == ref.shape == (n_res, 1) and bool(torch.isfinite(z).all())
+    assert (z - ref).abs().median().item() < 1e-3
+    m = cuda_models("i_v3_1", "f16x3")
+    zt = m(*args, n_res=n_res)
+    with pytest.raises(_lib.PestoError, match="fp16 operand planes"):
+        m.raise_if_failed()
+    assert bool(torch.isnan(zt).all())
+
+
+def test_runner_feeds_the_123_feature_models(cuda_models):
+    """predict_structures on a structure dictionary with resname / name columns == Model.forward on encode_features."""
+    from pesto_b200.runner import predict_structures
+    c, X, ids1, q0, rid, n_res = _v3_inputs()
+    s = {k: c[k] for k in ("element", "resname", "name", "resid")}
+    s["xyz"] = c["X"]
+    model = cuda_models("i_v3_0", "f16x3")
+    (idx, z), = list(predict_structures(model, [s]))
+    assert idx == 0 and z.shape == (n_res, 5)
+    assert (z - torch.from_numpy(c["z_i_v3_0"])).abs().max().item() < 1e-3

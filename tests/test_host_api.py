@@ -150,3 +150,29 @@ def test_empty_structure_is_rejected_before_any_device_work():
         extract_topology(torch.zeros((0, 3)), 64)
     with pytest.raises(ValueError):
         extract_topology(torch.zeros((5, 2)), 64)
+
+
+def test_feature_index_of_the_v3_models_and_head_depths():
+    """123-feature q0 (element | residue name | atom name one-hots) travels as three bytes per atom; a Model built for a
+    checkpoint takes the head depths from its keys (i_v3_1: single Linear em / dm, one logit)."""
+    from conftest import load_case, load_config, load_weights
+    from pesto_b200.data_encoding import encode_features
+    from pesto_b200.model import Model
+    from pesto_b200.runner import encode_batch, expand_features, feature_index
+    c = load_case("v3_1gpw_A")
+    s = {k: c[k] for k in ("element", "resname", "name", "resid")}
+    s["xyz"] = c["X"]
+    idx = feature_index(s, 123)
+    assert idx.shape == (len(c["X"]), 3) and idx.dtype == np.uint8 and np.array_equal(idx, c["feat"])
+    q0 = torch.cat(encode_features(s), dim=1)
+    assert q0.shape[1] == 123 and torch.equal(expand_features(torch.from_numpy(idx), 123), q0)
+    assert np.array_equal(encode_batch([s], n_features=123)[1], q0.numpy())
+    assert feature_index(s, 30).shape == (len(c["X"]), 1)
+    with pytest.raises(ValueError):
+        feature_index(s, 64)
+    for tag, depth, n_out in (("i_v3_0", 3, 5), ("i_v3_1", 1, 1)):
+        sd = {k: torch.from_numpy(v) for k, v in load_weights(tag).items()}
+        m = Model.for_state_dict(load_config(tag), sd)                     # strict load: the key sets agree
+        assert len(m.em) == (5 if depth == 3 else 1) and len(m.dm) == (5 if depth == 3 else 1) and m.num_out == n_out
+    with pytest.raises(RuntimeError):
+        Model(load_config("i_v3_1")).load_state_dict({k: torch.from_numpy(v) for k, v in load_weights("i_v3_1").items()})

@@ -46,6 +46,39 @@ def test_topology_batch_case():
         assert O.same_modulo_ties(ids, torch.from_numpy(c[f"ids0_{i}"]).long(), Xi)
 
 
+def v3_inputs():
+    from pesto_b200.runner import expand_features
+    c = load_case("v3_1gpw_A")
+    X, rid, n_res = torch.from_numpy(c["X"]), torch.from_numpy(c["rid"].astype(np.int64)), int(c["n_res"])
+    q0 = expand_features(torch.from_numpy(c["feat"]), 123)
+    ids1 = O.collate([(X, torch.from_numpy(c["ids0"]).long(), q0, rid, n_res)])[1]
+    return c, X, ids1, q0, rid, n_res
+
+
+def test_v3_0_forward_matches_reference():
+    """i_v3_0: 123 input features (element | residue name | atom name), 16 layers, three-layer heads."""
+    c, X, ids1, q0, rid, n_res = v3_inputs()
+    z = O.forward(load_weights("i_v3_0"), X, ids1, q0, rid, n_res)
+    ref = torch.from_numpy(c["z_i_v3_0"])
+    assert z.shape == ref.shape == (n_res, 5)
+    assert (z - ref).abs().max().item() < TOL
+
+
+def test_v3_1_forward_matches_reference_where_the_checkpoint_is_conditioned():
+    """i_v3_1 (single-Linear em / dm heads, one logit per residue; model/save/i_v3_1_2021-05-28_12-40/model.py).  The
+    shipped checkpoint lets the state grow to ~4e5 by layer 14, so its logits are ill-conditioned in fp32: the oracle in
+    fp64 and in fp32 differ by up to 8.6 on this structure, exactly like oracle and reference do.  Parity is therefore
+    pinned on the median residue (~1e-5), and on the state of the early layers through the hybrid test on the GPU."""
+    c, X, ids1, q0, rid, n_res = v3_inputs()
+    taps = {15: None}
+    z = O.forward(load_weights("i_v3_1"), X, ids1, q0, rid, n_res, taps=taps)
+    ref = torch.from_numpy(c["z_i_v3_1"])
+    assert z.shape == ref.shape == (n_res, 1)
+    d = (z - ref).abs()
+    assert d.median().item() < TOL
+    assert taps[15][0].abs().max().item() > 1e5           # the documented growth: beyond what fp16 operand planes hold
+
+
 @pytest.mark.parametrize("name,tag", [("tiny40", "i_v4_1"), ("tiny40", "i_v4_0"), ("batch3", "i_v4_0"),
                                       ("stale257", "i_v4_0"), ("synth517", "i_v4_0")])
 def test_forward_matches_reference(name, tag):
