@@ -477,6 +477,30 @@ def main():
                                  "edge_kernel_ms_by_nn": {str(k): float(np.mean(v)) for k, v in sorted(pn.items())},
                                  "node_kernel_ms": float(np.mean(nm)), "forward_ms": ms_f, "atoms_per_s": n_syn / (ms_f * 1e-3),
                                  "forward_frac": n_syn * 547328 / (ms_f * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                # configs[2]: i_v4_0 (16 layers) over a batch of 32 synthetic 8192-atom structures (262 144 atoms), one topology
+                # call + one forward per step
+                with open(os.path.join(GOLDEN, "config_i_v4_0.json")) as fh:
+                    m40 = Model.for_state_dict(json.load(fh), {k: torch.from_numpy(v) for k, v in
+                                                                 np.load(os.path.join(GOLDEN, "weights_i_v4_0.npz")).items()},
+                                               mode=args.mode).eval().to(dev)
+                parts = [synth_structure(8192, BASE_SEED + 100 + i) for i in range(32)]
+                Xb = torch.cat([p_[0] for p_ in parts]).to(dev)
+                qb = one_hot_features(torch.cat([p_[1] for p_ in parts])).to(dev)
+                nres_each = [int(p_[2].max()) + 1 for p_ in parts]
+                roff_b = np.concatenate([[0], np.cumsum(nres_each)])
+                ridb = torch.cat([p_[2] + int(roff_b[i]) for i, p_ in enumerate(parts)]).int().to(dev)
+                nres_b = int(roff_b[-1])
+                ids_b = batch_topology(Xb, [8192] * 32, 64)
+                for _ in range(2):
+                    m40(Xb, ids_b, qb, ridb, n_res=nres_b)
+                ms_knn = event_ms(lambda: batch_topology(Xb, [8192] * 32, 64), 5)
+                ms_b = event_ms(lambda: m40(Xb, ids_b, qb, ridb, n_res=nres_b), 5)
+                m40.raise_if_failed(dev)
+                by["configs[2] i_v4_0 (16 layers), batch of 32 x N=8192"] = {
+                    "n_atoms": int(Xb.shape[0]), "structures": 32, "forward_ms": ms_b, "topology_ms": ms_knn,
+                    "atoms_per_s": int(Xb.shape[0]) / (ms_b * 1e-3), "atoms_per_s_with_topology": int(Xb.shape[0]) / ((ms_b + ms_knn) * 1e-3),
+                    "forward_frac": int(Xb.shape[0]) * (547328 // 2) / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                del m40, Xb, qb, ridb, ids_b, parts
                 s0 = structs[0]
                 X1 = torch.from_numpy(s0["xyz"]).to(dev)
                 e1, r1 = encode_batch([s0], as_index=True)[1:3]
