@@ -329,6 +329,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     constexpr int GA = NN / 8;                      // 8-edge reduction groups per atom
     constexpr bool UMMA = NN >= 32;                 // U_i enters through spare K columns of the first MMA
     constexpr bool TPREF = NN >= 32;                // first T_j chunk loaded one tile ahead (measured slower at nn <= 16)
+    constexpr bool UEARLY = NN == 8;                // U_i loaded with T_j at the tile's start and added there: the loads' latency
+                                                    // is not paid once per chunk inside E1 (nn = 8: -3.4 %; nn = 16: +5 %, spills)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *img = smem_raw;                                      // weight images + biases (shared by both halves)
     const float *b2 = reinterpret_cast<const float *>(img + tcimg::BIAS);
@@ -681,6 +683,20 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         if (!TPREF)
 #endif
         load_T(j, 1);
+        if (UEARLY) {       // U_i of the row's atom, added to T_j while both are in flight (not between the chunks' waits)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int kr = 0; kr < 4; ++kr) {
+                    const int ik = min(tile * TA + (quarter * 32 + 8 * kr + rl) / NN, n_atoms - 1);
+                    float pu[8];
+                    tc::ldg256(nodeC + (size_t)(ik + 1) * NODE_C_STRIDE + 32 * (2 * grp + cc) + 8 * m4, pu);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        up2(add2(pk2(tv[cc][kr][2 * e], tv[cc][kr][2 * e + 1]), pk2(pu[2 * e], pu[2 * e + 1])),
+                            tv[cc][kr][2 * e], tv[cc][kr][2 * e + 1]);
+                }
+        }
         PROF_STAMP(4);
 
         // ---------------------------------------------------------------- E1: h1 = ELU(D1 + T_j [+ U_i]) -> A2 (X, in place)
@@ -695,7 +711,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     y[bk][kr][0] = pk2(tv[cc][kr][4 * bk], tv[cc][kr][4 * bk + 1]);
                     y[bk][kr][1] = pk2(tv[cc][kr][4 * bk + 2], tv[cc][kr][4 * bk + 3]);
                 }
-            if (!UMMA) {                                     // U_i of the row's atom (nn <= 16: not folded into the MMA)
+            if (!UMMA && !UEARLY) {                          // U_i of the row's atom (nn = 16: not folded into the MMA)
 #pragma unroll
                 for (int kr = 0; kr < 4; ++kr) {
                     const int ik = min(tile * TA + (quarter * 32 + 8 * kr + rl) / NN, n_atoms - 1);
@@ -1012,7 +1028,11 @@ int launch_edge_tc(const void *tcw, int n_atoms, const int32_t *ids32, const flo
                    const float *nodeT, const float *nodeC, float *Zout, cudaStream_t st, int *wd) {
     int n_sm = 0;
     // the debug timeline (pesto_debug_edge_timeline) exists for the parity mode's nn = 64 kernel only
+#ifdef PESTO_PROF_ALL_NN                            // measurement builds only (profiles/variants.py): timeline stamps for every nn
+    constexpr bool CAN_PROF = SPLIT;
+#else
     constexpr bool CAN_PROF = NN == 64 && SPLIT;
+#endif
     const bool prof_on = CAN_PROF && g_prof_buf != nullptr;
     auto kernel = prof_on ? edge_kernel_tc<NN, SPLIT, CAN_PROF> : edge_kernel_tc<NN, SPLIT, false>;
     { const int rc_ = device_setup((const void *)kernel, SM_TOTAL, &n_sm); if (rc_ != PESTO_OK) return rc_; }

@@ -15,10 +15,16 @@ from pesto_b200.synth import synth_structure, one_hot_features       # noqa: E40
 ap = argparse.ArgumentParser()
 ap.add_argument("--atoms", type=int, default=32768)
 ap.add_argument("--tiles", type=int, default=48)
+ap.add_argument("--layers", type=int, default=32, help="use the first LAYERS layers of i_v4_1: the timeline is the LAST launch's "
+                "(8 -> nn = 8, 16 -> nn = 16, 24 -> nn = 32; needs a -DPESTO_PROF_ALL_NN build, profiles/variants.py)")
 a = ap.parse_args()
 g = os.path.join(REPO, "tests", "golden")
-model = Model(json.load(open(os.path.join(g, "config_i_v4_1.json"))), mode="f16x3")
-model.load_state_dict({k: torch.from_numpy(v) for k, v in np.load(os.path.join(g, "weights_i_v4_1.npz")).items()})
+cfg = json.load(open(os.path.join(g, "config_i_v4_1.json")))
+cfg["sum"] = cfg["sum"][:a.layers]
+model = Model(cfg, mode="f16x3")
+model.load_state_dict({k: torch.from_numpy(v) for k, v in np.load(os.path.join(g, "weights_i_v4_1.npz")).items()
+                       if not k.startswith("sum.") or int(k.split(".")[1]) < a.layers})
+print(f"last layer: nn = {cfg['sum'][-1]['nn']}")
 model = model.eval().cuda()
 X, el, rid = synth_structure(a.atoms, 20230419)
 Xd = X.cuda()
