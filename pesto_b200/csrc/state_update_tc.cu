@@ -595,8 +595,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     // M1: D1 (X) = A1 . B1^T, K = 80, split by accumulator columns over M1S issuing warps (each a chain over 128 / M1S
     // columns with its own chunk commits).  An issuing warp is held back while the tensor-core queue drains -- and M1 is the
     // longest chain (0.9 k cycles) -- so one issuer arrives that much later at the reduction's barrier than the other seven
-    // warps; four issuers (warps 0, 2, 4, 6) are held back a quarter as long (+1.9 %; at nn = 8 one issuer measures better)
-    constexpr int M1S = NN >= 16 ? 4 : 1;
+    // warps; four issuers (warps 0, 2, 4, 6) are held back a quarter as long (+1.9 %; +2.4 % at nn = 8 since round 2)
+    constexpr int M1S = 4;
     auto issue_m1 = [&]() {
         constexpr int NC = 128 / M1S;                                   // columns per issuer
         if ((hwarp_u % (8 / M1S)) == 0 && tc::elect_one()) {
@@ -640,26 +640,15 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         const int i0 = min(tile0 * TA + a_loc, n_atoms - 1);
         j_next = ids32[(size_t)i0 * KMAX + k];
         g_next = geom[(size_t)i0 * KMAX + k];
-#ifdef PESTO_EXPERIMENT_ONE_HALF
-        if (H == 0)
-#endif
         {
             s0_compute(tile0, j_next, g_next);
             if (S0SPLIT && grp != 0) s0_store_pj();
             s0_store(tile0, g_next);
-            if (TPREF) {
-                load_T(j_next, 0);
-#ifdef PESTO_X_TPREF2B
-                load_T(j_next, 1);
-#endif
-            }
+            if (TPREF) load_T(j_next, 0);
             bar_named(bar_id, HALF_THREADS);
             issue_m1();
         }
     }
-#ifdef PESTO_EXPERIMENT_ONE_HALF
-    if (H == 0)
-#endif
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
         PROF_STAMP(0);
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
@@ -677,11 +666,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         PROF_STAMP(1);
         PROF_STAMP(2);
         PROF_STAMP(3);
-        // T_j: for nn >= 32 the first chunk (with PESTO_X_TPREF2B: both) was loaded one tile ahead, after the reduction loop
+        // T_j: for nn >= 32 the first chunk was loaded one tile ahead, after the reduction loop (both chunks ahead: slower)
         if (!TPREF) load_T(j, 0);
-#ifdef PESTO_X_TPREF2B
-        if (!TPREF)
-#endif
         load_T(j, 1);
         if (UEARLY) {       // U_i of the row's atom, added to T_j while both are in flight (not between the chunks' waits)
 #pragma unroll
@@ -731,8 +717,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         tc::wait_st();
         tc::fence_before_sync();
         PROF_STAMP(5);
-        bar_named(bar_id, HALF_THREADS);
-        PROF_STAMP(6);
+        bar_named(bar_id, HALF_THREADS);   // (per-group barriers here and before M3 -- M2 / M3 are block diagonal by group -- need an
+        PROF_STAMP(6);                     //  "all of M1 done" guard before M2 overwrites A1 in Y, and then measure +0.1 %: not kept)
         // M2: D2 (Y) = blockdiag(eqkm.2, epkm.2, evm.2).  Each column group issues the GEMMs it consumes itself (an issuing
         // warp is held back while the tensor-core queue drains, so it should only wait for its own results); separate
         // commits: the ELU stage of the first chunks overlaps the remaining MMAs
@@ -822,9 +808,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         // S0 arithmetic of the next tile in the shadow of this tile's third-layer MMA (unconditional for the same reason as
         // the T_j prefetch: on the last tile it recomputes this tile's words, which are never stored)
         s0_compute(more ? tile + tstride : tile, jn, gn);
-#ifdef PESTO_X_PJR2
-        PJR_LOAD();
-#endif
         if (alive) alive = tc::mbar_wait_a(bar0_a, ph0, wd, 3, max_spin);     // group 0: Kq | Kp; group 1: V0
         tc::fence_after_sync();
         PROF_STAMP(10);
@@ -929,9 +912,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             s0_store(tile + tstride, gn);
         }
         // p_j of the reduction group's 8 edges (phase R): issued before the barrier so that part of the gather latency overlaps it
-#ifndef PESTO_X_PJR2
         PJR_LOAD();
-#endif
         // ---------------------------------------------------------------- R: attention-weighted sums over the edges
         // thread = (8-edge group rg, channel pair): Zq = Mq . V0 (:143), Zp = Mp . [V1 (x) r ; p_i ; p_j] (:131-136, :144)
         {
@@ -990,9 +971,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
             if (TPREF) {          // unconditional (row 0 when there is no next tile): a load under `if (more)` would keep tv alive
                 load_T(jn, 0);    // -- and 32 registers occupied -- through the whole tile
-#ifdef PESTO_X_TPREF2B
-                load_T(jn, 1);
-#endif
             }
             bar_named(bar_id, HALF_THREADS);
             PROF_STAMP(14);

@@ -2,8 +2,8 @@
 """Experiment aid: build kernel variants of the tensor-core edge kernel side by side (here, on CPU) and compare them in
 ONE gpurun call (there).
 
-    python profiles/variants.py build base= tpref=PESTO_X_TPREF both=PESTO_X_TPREF,PESTO_X_S0PRE     # here
-    python profiles/variants.py run base tpref both                                                 # under gpurun
+    python profiles/variants.py build base= profall=PESTO_PROF_ALL_NN                                # here (name=DEFINE[,DEFINE...])
+    python profiles/variants.py run base profall                                                    # under gpurun
 
 `run` prints, per variant, the bench line's value / e2e / per-nn edge-kernel times and the logit error against the
 CPU oracle sample is NOT taken (--no-cpu-baseline); parity is checked separately with pytest on the chosen variant."""
