@@ -409,7 +409,7 @@ def main():
 
         # ---- the same job from structure dictionaries through the public many-structures runner: host encoding (element
         #      strings -> index, residue index), pinned H2D on a copy stream, kNN, forward, D2H, per-structure results
-        list(predict_structures(model, structs[:8], device=dev))                      # warm-up (pinned buffers)
+        list(predict_structures(model, structs, device=dev))                          # warm-up (pinned staging buffers sized for this shard)
         barrier()
         t0 = time.perf_counter()
         n_out = sum(int(z.shape[0]) for _, z in predict_structures(model, structs, device=dev))

@@ -202,12 +202,18 @@ __device__ __forceinline__ u64 elu2_scaled(u64 y, const PairConsts &k) {
     const u64 t = fma2(pk2(ex2_fast(n0), ex2_fast(n1)), k.c, k.negc);
     return add2(d, t);
 }
-// hi = bf16x2(x), lo = bf16x2(x - hi)
+// hi = h16x2(x), lo = h16x2(x - hi)
 template <bool SPLIT>
 __device__ __forceinline__ void split2(u64 x, const PairConsts &k, uint32_t &hi, uint32_t &lo) {
     float x0, x1;
     up2(x, x0, x1);
     hi = tc::pack_h16x2(x0, x1);
+    if (SPLIT && tc::H16_IS_FP16) {      // remainders by one mixed-precision FMA each (nn = 64 kernel -2.5 % against unpack + packed subtract)
+        float l0, l1;
+        tc::residual_f16x2(hi, x0, x1, l0, l1);
+        lo = tc::pack_h16x2(l0, l1);
+        return;
+    }
     if (SPLIT) {
         float h0, h1;
         tc::unpack_h16x2(hi, h0, h1);
@@ -329,6 +335,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     constexpr int GA = NN / 8;                      // 8-edge reduction groups per atom
     constexpr bool UMMA = NN >= 32;                 // U_i enters through spare K columns of the first MMA
     constexpr bool TPREF = NN >= 32;                // first T_j chunk loaded one tile ahead (measured slower at nn <= 16)
+    constexpr bool V0BIAS = NN == 64 || NN == 16;   // the attention weights Mq of an atom sum to one: the bias of V0 is added once per
+                                                    // atom to Zq instead of once per edge in E3 (nn = 64: -2.1 %, 16: -0.7 %; 8 / 32: +1 %)
     constexpr bool UEARLY = NN == 8;                // U_i loaded with T_j at the tile's start and added there: the loads' latency
                                                     // is not paid once per chunk inside E1 (nn = 8: -3.4 %; nn = 16: +5 %, spills)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -891,6 +899,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     tc::tmem_ld16(tlane + TX + 32 + 32 * half + 16 * q16, r);
                     tc::wait_ld();
                     float4 *dst = reinterpret_cast<float4 *>(Vs + e * VS_STRIDE + 32 * half + 16 * q16);
+                    if (V0BIAS && half == 0) {      // V0 without its bias (added once per atom to Zq in EP below)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            *reinterpret_cast<uint4 *>(dst + u) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+                        continue;
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const ulonglong2 bb = *reinterpret_cast<const ulonglong2 *>(b3 + 32 + 32 * half + 16 * q16 + 4 * u);
@@ -977,8 +991,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             // Z record of atom a: [Zq h*32+s | Zp c*64 + h*32 + s]; the per-atom projections qpm / ppm run in the next
             // node kernel, where their weights are reused across 8 atoms
 #pragma unroll
+            const float zb = V0BIAS && ht < 64 ? b3[32 + (ht & 31)] : 0.f;      // bias of V0 (evm.4 rows 0..31), both heads of Zq
+#pragma unroll
             for (int a = 0; a < TA; ++a) {
-                float z = 0.f;
+                float z = zb;
 #pragma unroll
                 for (int gg = 0; gg < GA; ++gg) z += Vs[(a * GA + gg) * 256 + ht];
                 const int io = tile * TA + a;

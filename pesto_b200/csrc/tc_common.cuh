@@ -335,6 +335,13 @@ __device__ __forceinline__ void unpack_h16x2(uint32_t w, float &a, float &b) {
         b = __uint_as_float(w & 0xffff0000u);
     }
 }
+// remainders a - float(w.lo), b - float(w.hi) of a packed fp16 word: one mixed-precision FMA each (FHFMA: f16 x f16 + f32,
+// the product w.x * -1 is exact, one rounding of an exactly representable difference) instead of two conversions and a subtract
+__device__ __forceinline__ void residual_f16x2(uint32_t w, float a, float b, float &la, float &lb) {
+    asm("{\n\t.reg .b16 l, h, m;\n\tmov.b32 {l, h}, %2;\n\tmov.b16 m, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, l, m, %3;\n\tfma.rn.f32.f16 %1, h, m, %4;\n\t}"
+        : "=f"(la), "=f"(lb) : "r"(w), "f"(a), "f"(b));
+}
 // one float -> 16-bit pattern and back (U planes)
 __device__ __forceinline__ uint16_t h16_from_f32(float f) { return (uint16_t)(pack_h16x2(f, 0.f) & 0xffffu); }
 __device__ __forceinline__ float h16_to_f32(uint16_t h) {
@@ -345,6 +352,12 @@ __device__ __forceinline__ float h16_to_f32(uint16_t h) {
 // hi = h16x2(a, b); lo = h16x2(a - float(hi.a), b - float(hi.b))
 __device__ __forceinline__ void split_h16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
     hi = pack_h16x2(a, b);
+    if (H16_IS_FP16) {
+        float ra, rb;
+        residual_f16x2(hi, a, b, ra, rb);
+        lo = pack_h16x2(ra, rb);
+        return;
+    }
     float ha, hb;
     unpack_h16x2(hi, ha, hb);
     unsigned long long x, h, l;                       // one packed subtract (FADD2) for the two remainders
