@@ -15,6 +15,7 @@ constexpr int SR = PESTO_STATE_STRIDE;  // 128 floats per atom record
 // The tensor-core path carries edge-MLP pre-activations scaled by log2(e) so that ELU is a bare ex2 (state_update_tc.cu)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float ILOG2E = 0.6931471805599453f;
+constexpr float ELU_K = 3.9216517136564484f;          // log2(e) * 2^log2(e) = log2(e) * e (shifted ELU of the tensor-core edge kernel)
 
 // ---------------------------------------------------------------------------------------------
 // Per-layer packed weights (float offsets inside one layer block).  "T" = stored transposed,

@@ -97,7 +97,7 @@ void pack_node_tc_layer(const float *blob, void *dst_v) {
         tb[64 + i] = blob[L::O_Q3B + i];
     }
     float *hb = (float *)(dst + nimg::H_BIAS);
-    for (int i = 0; i < 128; ++i) hb[i] = LOG2E * blob[L::N_BU + i];
+    for (int i = 0; i < 128; ++i) hb[i] = LOG2E * blob[L::N_BU + i] - LOG2E;      // (-c: the edge kernel's first E-stage takes shifted input)
     for (int i = 0; i < 32; ++i) {
         hb[128 + i] = blob[L::NQ_B1 + i];
         hb[160 + i] = blob[L::NQ_B2 + i];

@@ -111,17 +111,31 @@ void pack_tc_layer(const float *blob, void *dst_v) {
             put(tcimg::B2V, 64, n, k, blob[L::E_2V + kpos_channel(k) * 64 + col_channel(n)]);
             put(tcimg::B3V, 64, n, k, ILOG2E * blob[L::E_3V + kpos_channel(k) * 64 + n]);
         }
-    float *bias = (float *)(dst + tcimg::BIAS);        // natural channel order (threads index them by channel)
-    for (int i = 0; i < 32; ++i) {
-        bias[i] = LOG2E * blob[L::E_2QB + i];
-        bias[32 + i] = LOG2E * blob[L::E_2PB + i];
+    // Biases, natural channel order (threads index them by channel).  The E-stages work on shifted activations (elu2_shifted):
+    // a stage's input carries -c, its output +c, so b2' = c b2 - c - c rowsum(W2) and b3' = b3 - c rowsum(W3 / c), the row sums
+    // taken over the operand planes as stored (hi + lo), i.e. over what the tensor core multiplies the +c by
+    auto stored = [&](int img_off, int N, int n, int k) {
+        const size_t e = (size_t)(k / 8) * N * 8 + (size_t)n * 8 + (k % 8);
+        return (double)tc::h16_to_f32_host(((const uint16_t *)(dst + img_off))[e]) +
+               (double)tc::h16_to_f32_host(((const uint16_t *)(dst + tcimg::IMG + img_off))[e]);
+    };
+    auto rowsum = [&](int img_off, int N, int n, int K) {
+        double t = 0.0;
+        for (int k = 0; k < K; ++k) t += stored(img_off, N, n, k);
+        return t;
+    };
+    float *bias = (float *)(dst + tcimg::BIAS);
+    const double c = (double)LOG2E;
+    for (int n = 0; n < 32; ++n) {                     // accumulator column n <-> channel col_channel(n)
+        bias[col_channel(n)] = (float)(c * blob[L::E_2QB + col_channel(n)] - c - c * rowsum(tcimg::B2Q, 32, n, 32));
+        bias[32 + col_channel(n)] = (float)(c * blob[L::E_2PB + col_channel(n)] - c - c * rowsum(tcimg::B2P, 32, n, 32));
     }
-    for (int i = 0; i < 64; ++i) {
-        bias[64 + i] = LOG2E * blob[L::E_2VB + i];
-        bias[128 + 32 + i] = blob[L::E_3VB + i];
+    for (int n = 0; n < 64; ++n) {
+        bias[64 + col_channel(n)] = (float)(c * blob[L::E_2VB + col_channel(n)] - c - c * rowsum(tcimg::B2V, 64, n, 64));
+        bias[128 + 32 + n] = (float)(blob[L::E_3VB + n] - c * rowsum(tcimg::B3V, 64, n, 64));
     }
-    for (int i = 0; i < 3; ++i) bias[128 + i] = blob[L::E_3QB + i];
-    for (int i = 0; i < 9; ++i) bias[128 + 16 + i] = blob[L::E_3PB + i];
+    for (int i = 0; i < 3; ++i) bias[128 + i] = (float)(blob[L::E_3QB + i] - c * rowsum(tcimg::B3Q, 16, i, 32));
+    for (int i = 0; i < 9; ++i) bias[128 + 16 + i] = (float)(blob[L::E_3PB + i] - c * rowsum(tcimg::B3P, 16, i, 32));
 }
 
 namespace {
@@ -186,21 +200,25 @@ __device__ __forceinline__ float ex2_fast(float x) {     // one MUFU; inputs bel
     return t;
 }
 __device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * LOG2E); }
+__device__ __forceinline__ float rcp_fast(float x) {     // one MUFU (normal, finite x)
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
 
 struct PairConsts {
-    u64 neg1, c, negc;     // (-1,-1), (log2e, log2e), (-log2e, -log2e)
+    u64 neg1, k;           // (-1,-1), (c 2^c, c 2^c) with c = log2(e)
 };
 
-// Activations travel scaled by c = log2(e) (folded into the weight images): with y = c x,
-//   c ELU(x) = (y - min(y,0)) + c (2^min(y,0) - 1)
-// exact for y > 0; one MUFU, one FMNMX and 1.5 packed FMA-pipe instructions per element.
-__device__ __forceinline__ u64 elu2_scaled(u64 y, const PairConsts &k) {
-    float y0, y1;
-    up2(y, y0, y1);
-    const float n0 = fminf(y0, 0.f), n1 = fminf(y1, 0.f);
-    const u64 d = fma2(pk2(n0, n1), k.neg1, y);
-    const u64 t = fma2(pk2(ex2_fast(n0), ex2_fast(n1)), k.c, k.negc);
-    return add2(d, t);
+// Activations travel scaled by c = log2(e) and shifted: a stage receives u = c x - c (the -c sits in the bias it adds: U_i
+// for the first layer, b2' / b3' below) and hands on c ELU(x) + c (the next GEMM's bias takes c * rowsum(W) back out):
+//   n = min(u, -c);   c ELU(x) + c = (u - n) + c 2^c 2^n        (u <= -c: c 2^(c x);  u > -c: c x + c)
+// one FMNMX, one MUFU and one packed FMA-pipe instruction per element (the unshifted form needs half an instruction more).
+__device__ __forceinline__ u64 elu2_shifted(u64 u, const PairConsts &k) {
+    float u0, u1;
+    up2(u, u0, u1);
+    const float n0 = fminf(u0, -LOG2E), n1 = fminf(u1, -LOG2E);
+    return fma2(pk2(ex2_fast(n0), ex2_fast(n1)), k.k, fma2(pk2(n0, n1), k.neg1, u));
 }
 // hi = h16x2(x), lo = h16x2(x - hi)
 template <bool SPLIT>
@@ -302,7 +320,7 @@ __device__ __forceinline__ void estage_finish(uint32_t tchunk, u64 (&y)[2][4][2]
 #pragma unroll
         for (int kr = 0; kr < 4; ++kr)
 #pragma unroll
-            for (int w = 0; w < 2; ++w) split2<SPLIT>(elu2_scaled(y[bk][kr][w], k), k, hi[bk][kr][w], lo[bk][kr][w]);
+            for (int w = 0; w < 2; ++w) split2<SPLIT>(elu2_shifted(y[bk][kr][w], k), k, hi[bk][kr][w], lo[bk][kr][w]);
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const uint32_t ta = tchunk + ((uint32_t)(16 * hb) << 16);
@@ -416,8 +434,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     const uint32_t max_spin = dbg ? 1u << 6 : 1u << 20;
     PairConsts kc;
     kc.neg1 = pk2(-1.f, -1.f);
-    kc.c = pk2(LOG2E, LOG2E);
-    kc.negc = pk2(-LOG2E, -LOG2E);
+    kc.k = pk2(ELU_K, ELU_K);
 
     const int n_tiles = (n_atoms + TA - 1) / TA;
     const int e = ht & 127;                                        // edge slot inside the tile = TMEM lane
@@ -871,7 +888,11 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 const float4 o = *reinterpret_cast<const float4 *>(red + (quarter ^ 1) * 8 + 4);
                 sm[0] += o.x; sm[1] += o.y; sm[2] += o.z; sm[3] += o.w;
             }
-            const float iq0 = 1.0f / sm[0], iq1 = 1.0f / sm[1], ip0 = 1.0f / sm[2], ip1 = 1.0f / sm[3];
+            // the sums lie in [1, 3 nn] (the largest term is exp(0)): one MUFU.RCP each (<= 1 ulp) instead of the IEEE division
+            // with its range fix-up code where that measures faster (nn <= 32: -0.6 .. -1.2 % per launch; nn = 64: +1 %)
+            constexpr bool RCP = NN <= 32;
+            const float iq0 = RCP ? rcp_fast(sm[0]) : 1.0f / sm[0], iq1 = RCP ? rcp_fast(sm[1]) : 1.0f / sm[1];
+            const float ip0 = RCP ? rcp_fast(sm[2]) : 1.0f / sm[2], ip1 = RCP ? rcp_fast(sm[3]) : 1.0f / sm[3];
             const float wq0 = eq[0] * iq0, wq1 = eq[1] * iq1;                     // Mq[h]
             const float wv0 = ep[0][0] * ip0, wv1 = ep[1][0] * ip1;               // Mp[h, token V1 (x) r]
             const float wi0 = ep[0][1] * ip0, wi1 = ep[1][1] * ip1;               // Mp[h, token p_i]
