@@ -113,6 +113,26 @@ def test_knn_box_pruning_is_exact_for_any_atom_order():
     assert torch.equal(ids1, O.collate(parts)[1])
 
 
+def test_knn_large_structure_against_brute_force():
+    """32 768 atoms (1 024 chunk boxes, 32 box groups per query): the selected neighbours' distances equal the 64 smallest of
+    a brute-force distance matrix computed block by block on the device (fp64), row by row."""
+    from pesto_b200.data_encoding import extract_topology
+    X, _, _ = synth_structure(32768, BASE_SEED + 9)
+    Xd = X.cuda()
+    ids, d, _, _, _ = extract_topology(Xd, 64)
+    assert ids.shape == (32768, 64) and int(ids.min()) >= 0 and int(ids.max()) < 32768
+    assert bool((ids != torch.arange(32768, device="cuda").unsqueeze(1)).all())          # the atom itself is masked (D < 1e-2)
+    assert bool((d[:, 1:] >= d[:, :-1]).all())                                            # sorted by distance
+    X64 = Xd.double()
+    for r0 in range(0, 32768, 4096):
+        D = torch.cdist(X64[r0:r0 + 4096], X64)                                           # [4096, 32768] fp64
+        D[torch.arange(4096, device="cuda"), torch.arange(r0, r0 + 4096, device="cuda")] = float("inf")
+        best = torch.topk(D, 64, dim=1, largest=False).values
+        mine = torch.gather(D, 1, ids[r0:r0 + 4096])
+        assert (mine - best).abs().max().item() < 1e-4, r0
+        assert (d[r0:r0 + 4096].double() - best).abs().max().item() < 1e-4, r0
+
+
 def test_batch_topology_equals_collate_of_per_structure_knn():
     """One launch over a batch of structures == per-structure topology + collate (index shift, sink padding)."""
     from pesto_b200.data_encoding import batch_topology
