@@ -88,7 +88,8 @@ void pack_node_tc_layer(const float *blob, void *dst_v) {
             put2(dst + nimg::T_WQ3, 2048, 32, n, p, blob[L::O_Q3 + kr * 32 + n]);
             put2(dst + nimg::H_WN2, 2048, 32, n, p, blob[L::NQ_W2 + kr * 32 + n]);
         }
-        for (int n = 0; n < 16; ++n) put2(dst + nimg::H_WN3, 1024, 16, n, p, blob[L::NQ_W3 + kr * 16 + n]);
+        // queries in log2(e) units: the edge kernel's softmax takes 2^(logit - max) straight from MUFU.EX2
+        for (int n = 0; n < 16; ++n) put2(dst + nimg::H_WN3, 1024, 16, n, p, LOG2E * blob[L::NQ_W3 + kr * 16 + n]);
     }
     float *tb = (float *)(dst + nimg::T_BIAS);
     for (int i = 0; i < 32; ++i) {
@@ -102,7 +103,7 @@ void pack_node_tc_layer(const float *blob, void *dst_v) {
         hb[128 + i] = blob[L::NQ_B1 + i];
         hb[160 + i] = blob[L::NQ_B2 + i];
     }
-    for (int i = 0; i < 16; ++i) hb[192 + i] = blob[L::NQ_B3 + i];
+    for (int i = 0; i < 16; ++i) hb[192 + i] = LOG2E * blob[L::NQ_B3 + i];
 }
 
 namespace {

@@ -199,7 +199,6 @@ __device__ __forceinline__ float ex2_fast(float x) {     // one MUFU; inputs bel
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
     return t;
 }
-__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * LOG2E); }
 __device__ __forceinline__ float rcp_fast(float x) {     // one MUFU (normal, finite x)
     float t;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
@@ -874,9 +873,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             float eq[NH], ep[NH][3], sm[4];
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-                eq[h] = exp_fast(lq[h] - mx[h]);
+                eq[h] = ex2_fast(lq[h] - mx[h]);                  // (Q arrives scaled by log2(e) from the per-atom kernel)
 #pragma unroll
-                for (int gk = 0; gk < 3; ++gk) ep[h][gk] = exp_fast(lp[h][gk] - mx[2 + h]);
+                for (int gk = 0; gk < 3; ++gk) ep[h][gk] = ex2_fast(lp[h][gk] - mx[2 + h]);
             }
             sm[0] = seg_sum_tc<SEG>(eq[0]);
             sm[1] = seg_sum_tc<SEG>(eq[1]);
