@@ -149,15 +149,21 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 H, 256 H + 256): X = +0, Y = +128
 constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
-constexpr int WS_STRIDE = 28;         // floats per edge row of the attention-weight buffer (112 B: conflict-free STS.128)
+constexpr int WS_STRIDE = 12;         // floats per edge row of the attention-weight buffer: 11 single weights (48 B: conflict-free
+                                      // STS.128); FFMA2 takes them as scalar multipliers.  Round 1 stored every weight as a pair
+                                      // (112 B rows): 5.5 instead of 3 loads per edge and thread -- shared-memory traffic, not
+                                      // arithmetic, was the cost (all four nn variants -4 .. -6 % with the single weights)
+constexpr int WS_GROUP = 8 * WS_STRIDE + 4;      // floats per 8-edge reduction group: 4 floats of skew, so that the two groups a
+                                                 // warp reads in one broadcast load sit in different banks (+0.2 %)
 constexpr int PROF_STAMPS = 19;       // clock stamps per tile of the debug timeline (pesto_debug_edge_timeline)
 
 // per-half shared memory (byte offsets)
 constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64..79: W_d (hi), U planes per tile, W_d (lo)
 constexpr int HS_VS = HS_EXT_HI + 4096;                       // [128][VS_STRIDE] fp32 (E3 -> R); aliased by the partial sums P
-constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [128][WS_STRIDE] fp32 attention weights (E3 -> R)
-constexpr int HS_RED = HS_WS + 128 * WS_STRIDE * 4;           // [4 quarters][8] softmax exchange (nn = 64)
-constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;
+constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [16 groups][WS_GROUP] fp32 attention weights (E3 -> R)
+constexpr int HS_RED = HS_WS + 16 * WS_GROUP * 4;             // [4 quarters][8] softmax exchange (nn = 64)
+constexpr int HS_P = HS_VS;                                   // partial sums of R alias Vs (a buffer of their own saves a barrier but takes
+constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;                  // the CTA past the 196 KB carve-out: 28 KB of L1 left for the gathers, nn = 64 +3.8 %)
 constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
 constexpr int SM_HALF0 = SM_PAT + 128;
 constexpr int SM_BAR = SM_HALF0 + 2 * HS_BYTES;               // per half: 4 MMA chunk mbarriers (+ 1 spare); TMEM slot
@@ -374,6 +380,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     unsigned char *ext_hi = hs + HS_EXT_HI;
     float *Vs = reinterpret_cast<float *>(hs + HS_VS);
     float *Ws = reinterpret_cast<float *>(hs + HS_WS);
+    float *Ps = reinterpret_cast<float *>(hs + HS_P);
     float *red = reinterpret_cast<float *>(hs + HS_RED);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + SM_BAR) + 5 * H;     // [0..3]: column chunks
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + SM_BAR + 80);
@@ -896,13 +903,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             const float wv0 = ep[0][0] * ip0, wv1 = ep[1][0] * ip1;               // Mp[h, token V1 (x) r]
             const float wi0 = ep[0][1] * ip0, wi1 = ep[1][1] * ip1;               // Mp[h, token p_i]
             const float wj0 = ep[0][2] * ip0, wj1 = ep[1][2] * ip1;               // Mp[h, token p_j]
-            float4 *row = reinterpret_cast<float4 *>(Ws + e * WS_STRIDE);
-            row[0] = make_float4(wq0, wq0, wq1, wq1);
-            row[1] = make_float4(wj0, wj0, wj1, wj1);
-            row[2] = make_float4(wv0 * g.x, wv0 * g.x, wv0 * g.y, wv0 * g.y);
-            row[3] = make_float4(wv0 * g.z, wv0 * g.z, wv1 * g.x, wv1 * g.x);
-            row[4] = make_float4(wv1 * g.y, wv1 * g.y, wv1 * g.z, wv1 * g.z);
-            row[5] = make_float4(wi0, wi1, 0.f, 0.f);
+            float4 *row = reinterpret_cast<float4 *>(Ws + (e >> 3) * WS_GROUP + (e & 7) * WS_STRIDE);      // 11 weights, single: FFMA2 takes a scalar multiplier
+            row[0] = make_float4(wq0, wq1, wj0, wj1);
+            row[1] = make_float4(wv0 * g.x, wv0 * g.y, wv0 * g.z, wv1 * g.x);
+            row[2] = make_float4(wv1 * g.y, wv1 * g.z, wi0, wi1);
         } else {
             // V0 | V1 (+ bias) of this edge -> Vs row
 #pragma unroll
@@ -961,29 +965,31 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
 #pragma unroll
             for (int c = 0; c < 3; ++c) zp[c][0] = zp[c][1] = 0ull;
             const float *vrow = Vs + (rg * 8) * VS_STRIDE + 2 * pair;
-            const float *wrow = Ws + (rg * 8) * WS_STRIDE;
+            const float *wrow = Ws + rg * WS_GROUP;
+            float wis0 = 0.f, wis1 = 0.f;
 #pragma unroll
             for (int ee = 0; ee < 8; ++ee) {
-                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wrow + ee * WS_STRIDE);
-                const ulonglong2 c0 = wr[0], c1 = wr[1], c2 = wr[2], c3 = wr[3], c4 = wr[4];
-                const u64 c5 = *reinterpret_cast<const u64 *>(wr + 5);
+                const float4 *wr = reinterpret_cast<const float4 *>(wrow + ee * WS_STRIDE);
+                const float4 a = wr[0], b = wr[1], c = wr[2];
                 const u64 v0 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE);
                 const u64 v1 = *reinterpret_cast<const u64 *>(vrow + ee * VS_STRIDE + 32);
-                zq[0] = fma2(c0.x, v0, zq[0]);
-                zq[1] = fma2(c0.y, v0, zq[1]);
-                zp[0][0] = fma2(c2.x, v1, zp[0][0]);
-                zp[1][0] = fma2(c2.y, v1, zp[1][0]);
-                zp[2][0] = fma2(c3.x, v1, zp[2][0]);
-                zp[0][1] = fma2(c3.y, v1, zp[0][1]);
-                zp[1][1] = fma2(c4.x, v1, zp[1][1]);
-                zp[2][1] = fma2(c4.y, v1, zp[2][1]);
+                zq[0] = fma2(pk2(a.x, a.x), v0, zq[0]);
+                zq[1] = fma2(pk2(a.y, a.y), v0, zq[1]);
+                zp[0][0] = fma2(pk2(b.x, b.x), v1, zp[0][0]);
+                zp[1][0] = fma2(pk2(b.y, b.y), v1, zp[1][0]);
+                zp[2][0] = fma2(pk2(b.z, b.z), v1, zp[2][0]);
+                zp[0][1] = fma2(pk2(b.w, b.w), v1, zp[0][1]);
+                zp[1][1] = fma2(pk2(c.x, c.x), v1, zp[1][1]);
+                zp[2][1] = fma2(pk2(c.y, c.y), v1, zp[2][1]);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    zp[c][0] = fma2(c1.x, pjr[ee][c], zp[c][0]);
-                    zp[c][1] = fma2(c1.y, pjr[ee][c], zp[c][1]);
+                for (int cc = 0; cc < 3; ++cc) {
+                    zp[cc][0] = fma2(pk2(a.z, a.z), pjr[ee][cc], zp[cc][0]);
+                    zp[cc][1] = fma2(pk2(a.w, a.w), pjr[ee][cc], zp[cc][1]);
                 }
-                wi = add2(wi, c5);
+                wis0 += c.z;
+                wis1 += c.w;
             }
+            wi = pk2(wis0, wis1);
             float wi0, wi1;
             up2(wi, wi0, wi1);
             const u64 w0 = pk2(wi0, wi0), w1 = pk2(wi1, wi1);
@@ -995,7 +1001,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             }
             PROF_STAMP(13);
             bar_named(bar_id, HALF_THREADS);          // every read of Vs is done: the partial sums P alias it
-            u64 *P = reinterpret_cast<u64 *>(Vs + rg * 256 + 2 * pair);
+            u64 *P = reinterpret_cast<u64 *>(Ps + rg * 256 + 2 * pair);
             P[0] = zq[0];
             P[16] = zq[1];
 #pragma unroll
@@ -1016,7 +1022,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int a = 0; a < TA; ++a) {
                 float z = zb;
 #pragma unroll
-                for (int gg = 0; gg < GA; ++gg) z += Vs[(a * GA + gg) * 256 + ht];
+                for (int gg = 0; gg < GA; ++gg) z += Ps[(a * GA + gg) * 256 + ht];
                 const int io = tile * TA + a;
                 if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
             }
