@@ -251,6 +251,11 @@ __device__ __forceinline__ void bar_named(int id, int count) { asm volatile("bar
 
 template <int SEG>
 __device__ __forceinline__ float seg_max_tc(float v) {
+    if (SEG == 32) {      // whole warp: one warp-wide reduction instruction (redux.sync.max.f32 -> CREDUX.MAX.F32, sm_100a)
+        float r;          // instead of five shuffle + max steps (nn = 32: -0.7 %)
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+        return r;
+    }
 #pragma unroll
     for (int o = SEG / 2; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLM, v, o));
     return v;
