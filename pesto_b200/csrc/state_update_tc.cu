@@ -149,6 +149,8 @@ constexpr unsigned FULLM = 0xffffffffu;
 constexpr uint32_t TM_COLS = 512;     // TMEM columns per CTA; half H owns [256 H, 256 H + 256): X = +0, Y = +128
 constexpr uint32_t TX = 0, TY = 128;
 constexpr int VS_STRIDE = 68;         // floats per edge row of the V0|V1 staging buffer (272 B: conflict-free STS.128)
+constexpr int P_STRIDE = 8 * VS_STRIDE;        // floats between the partial sums (256 per 8-edge group) of two groups: each group's
+                                               // sums alias its own eight V rows
 constexpr int WS_STRIDE = 12;         // floats per edge row of the attention-weight buffer: 11 single weights (48 B: conflict-free
                                       // STS.128); FFMA2 takes them as scalar multipliers.  Round 1 stored every weight as a pair
                                       // (112 B rows): 5.5 instead of 3 loads per edge and thread -- shared-memory traffic, not
@@ -162,7 +164,7 @@ constexpr int HS_EXT_HI = 0;                                  // B1 rows k = 64.
 constexpr int HS_VS = HS_EXT_HI + 4096;                       // [128][VS_STRIDE] fp32 (E3 -> R); aliased by the partial sums P
 constexpr int HS_WS = HS_VS + 128 * VS_STRIDE * 4;            // [16 groups][WS_GROUP] fp32 attention weights (E3 -> R)
 constexpr int HS_RED = HS_WS + 16 * WS_GROUP * 4;             // [4 quarters][8] softmax exchange (nn = 64)
-constexpr int HS_P = HS_VS;                                   // partial sums of R alias Vs (a buffer of their own saves a barrier but takes
+constexpr int HS_P = HS_VS;                                   // partial sums of R alias Vs (a buffer of their own takes
 constexpr int HS_BYTES = HS_RED + 4 * 8 * 4;                  // the CTA past the 196 KB carve-out: 28 KB of L1 left for the gathers, nn = 64 +3.8 %)
 constexpr int SM_PAT = tcimg::TOTAL;                          // [TA <= 4][8] indicator words of the U columns
 constexpr int SM_HALF0 = SM_PAT + 128;
@@ -1005,8 +1007,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                 zp[c][1] = fma2(w1, pi, zp[c][1]);
             }
             PROF_STAMP(13);
-            bar_named(bar_id, HALF_THREADS);          // every read of Vs is done: the partial sums P alias it
-            u64 *P = reinterpret_cast<u64 *>(Ps + rg * 256 + 2 * pair);
+            __syncwarp();                             // the partial sums of a reduction group overwrite that group's OWN eight V rows,
+                                                      // which only its 16 threads (half of this warp) read: no half-wide barrier
+            u64 *P = reinterpret_cast<u64 *>(Ps + rg * P_STRIDE + 2 * pair);
             P[0] = zq[0];
             P[16] = zq[1];
 #pragma unroll
@@ -1027,7 +1030,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int a = 0; a < TA; ++a) {
                 float z = zb;
 #pragma unroll
-                for (int gg = 0; gg < GA; ++gg) z += Ps[(a * GA + gg) * 256 + ht];
+                for (int gg = 0; gg < GA; ++gg) z += Ps[(a * GA + gg) * P_STRIDE + ht];
                 const int io = tile * TA + a;
                 if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
             }
