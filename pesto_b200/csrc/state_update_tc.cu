@@ -367,6 +367,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     constexpr bool TPREF = NN >= 32;                // first T_j chunk loaded one tile ahead (measured slower at nn <= 16)
     constexpr bool V0BIAS = NN == 64 || NN == 16;   // the attention weights Mq of an atom sum to one: the bias of V0 is added once per
                                                     // atom to Zq instead of once per edge in E3 (nn = 64: -2.1 %, 16: -0.7 %; 8 / 32: +1 %)
+    constexpr bool EPLATE = NN <= 16;               // tile epilogue (8 / 16 atoms) deferred into the next tile, where barrier B orders the
+                                                    // partial sums: one half-wide barrier less (nn = 8: -5.7 %, 16: -1.8 %; nn >= 32: +3.5 %,
+                                                    // the epilogue delays the short second-layer stage there)
     constexpr bool UEARLY = NN == 8;                // U_i loaded with T_j at the tile's start and added there: the loads' latency
                                                     // is not paid once per chunk inside E1 (nn = 8: -3.4 %; nn = 16: +5 %, spills)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -687,6 +690,20 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             issue_m1();
         }
     }
+    // Tile epilogue: Z record of atom a = [Zq h*32+s | Zp c*64 + h*32 + s], the sum of the reduction groups' partial sums; the
+    // per-atom projections qpm / ppm run in the next node kernel, where their weights are reused across 8 atoms
+    const float zb = V0BIAS && ht < 64 ? b3[32 + (ht & 31)] : 0.f;      // bias of V0 (evm.4 rows 0..31), both heads of Zq
+    auto epilogue = [&](int t) {
+#pragma unroll
+        for (int a = 0; a < TA; ++a) {
+            float z = zb;
+#pragma unroll
+            for (int gg = 0; gg < GA; ++gg) z += Ps[(a * GA + gg) * P_STRIDE + ht];
+            const int io = t * TA + a;
+            if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
+        }
+    };
+    int ep_tile = -1;
     for (int tile = tile0; tile < n_tiles; tile += tstride) {
         PROF_STAMP(0);
         const int i = min(tile * TA + a_loc, n_atoms - 1);         // tail tile: clamp (results are not written)
@@ -776,6 +793,9 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         ph0 ^= 1u;
         ph1 ^= 1u;
         PROF_STAMP(7);
+        // nn <= 16: the previous tile's epilogue, in the shadow of this tile's second-layer MMAs: every warp has passed barrier B,
+        // so all partial sums are written (they sit in the V buffer, which is not written again before barrier C)
+        if (EPLATE && ep_tile >= 0) epilogue(ep_tile);
 
         // ---------------------------------------------------------------- E2: h2 = ELU(D2 + b2) -> A3 (Y, in place)
 #pragma unroll
@@ -1020,19 +1040,12 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             if (TPREF) {          // unconditional (row 0 when there is no next tile): a load under `if (more)` would keep tv alive
                 load_T(jn, 0);    // -- and 32 registers occupied -- through the whole tile
             }
-            bar_named(bar_id, HALF_THREADS);
-            PROF_STAMP(14);
-            // Z record of atom a: [Zq h*32+s | Zp c*64 + h*32 + s]; the per-atom projections qpm / ppm run in the next
-            // node kernel, where their weights are reused across 8 atoms
-#pragma unroll
-            const float zb = V0BIAS && ht < 64 ? b3[32 + (ht & 31)] : 0.f;      // bias of V0 (evm.4 rows 0..31), both heads of Zq
-#pragma unroll
-            for (int a = 0; a < TA; ++a) {
-                float z = zb;
-#pragma unroll
-                for (int gg = 0; gg < GA; ++gg) z += Ps[(a * GA + gg) * P_STRIDE + ht];
-                const int io = tile * TA + a;
-                if (io < n_atoms) Zout[(size_t)(io + 1) * 256 + ht] = z;
+            if (EPLATE) {
+                ep_tile = tile;   // the tile's epilogue runs after barrier B of the half's next tile (or after the loop)
+            } else {
+                bar_named(bar_id, HALF_THREADS);
+                PROF_STAMP(14);
+                epilogue(tile);
             }
         }
         PROF_STAMP(15);
@@ -1043,6 +1056,10 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
         g_next = gn;
     }
 #undef PROF_STAMP
+    if (EPLATE && ep_tile >= 0) {                      // the half's last tile
+        bar_named(bar_id, HALF_THREADS);
+        epilogue(ep_tile);
+    }
     tc::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc::tmem_dealloc(*tmem_slot, TM_COLS);
