@@ -470,7 +470,7 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
     // while the reduction phase R of the previous tile occupies the CUDA cores.
     // nn = 64: the p_j . r gather of a tile is shared by the two column groups (one gather round trip each instead of two on
     // the group that also computes the attention weights): -2 % there; at nn <= 32 the extra live words spill and it loses
-    constexpr bool S0SPLIT = NN == 64;
+    constexpr bool S0SPLIT = NN == 64;              // (re-measured at the end of round 2 for nn = 32 and all nn: no gain)
     uint32_t s0h[16], s0l[16];          // group 0 (!S0SPLIT): p_j . r words of all four row groups; group 1: p_i . r words
     uint32_t s0ph[8], s0pl[8];          // S0SPLIT: p_j . r words of this thread's two row groups (group g: 2g, 2g + 1)
     float u0v[UMMA ? TA : 1];
