@@ -993,7 +993,6 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
             for (int c = 0; c < 3; ++c) zp[c][0] = zp[c][1] = 0ull;
             const float *vrow = Vs + (rg * 8) * VS_STRIDE + 2 * pair;
             const float *wrow = Ws + rg * WS_GROUP;
-            float wis0 = 0.f, wis1 = 0.f;
 #pragma unroll
             for (int ee = 0; ee < 8; ++ee) {
                 const float4 *wr = reinterpret_cast<const float4 *>(wrow + ee * WS_STRIDE);
@@ -1013,10 +1012,8 @@ edge_kernel_tc(const unsigned char *__restrict__ tcw, int n_atoms, const int32_t
                     zp[cc][0] = fma2(pk2(a.z, a.z), pjr[ee][cc], zp[cc][0]);
                     zp[cc][1] = fma2(pk2(a.w, a.w), pjr[ee][cc], zp[cc][1]);
                 }
-                wis0 += c.z;
-                wis1 += c.w;
+                wi = add2(wi, pk2(c.z, c.w));             // (the last two words of the row's third load: an aligned register pair)
             }
-            wi = pk2(wis0, wis1);
             float wi0, wi1;
             up2(wi, wi0, wi1);
             const u64 w0 = pk2(wi0, wi0), w1 = pk2(wi1, wi1);
