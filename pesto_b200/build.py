@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpesto_b200.so")
-SOURCES = ["cabi.cu", "knn.cu", "prologue.cu", "state_update.cu", "state_update_tc.cu", "node_tc.cu", "node_umma.cu", "pool.cu", "pdb_io.cu", "rmma_probe.cu"]
+SOURCES = ["cabi.cu", "knn.cu", "prologue.cu", "state_update.cu", "state_update_tc.cu", "node_umma.cu", "pool.cu", "pdb_io.cu", "rmma_probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -163,8 +163,6 @@ int launch_state_update_fp32(const float *layer_w, int nn, int n_atoms, const in
                              const float *state_in, float *state_out, float *node_scratch, cudaStream_t st,
                              cudaEvent_t *ev = nullptr);
 int launch_node(const float *layer_w, int n_atoms, const float *state_in, float *node_scratch, cudaStream_t st);
-int launch_node_fused(const float *lw_prev, const float *lw_next, const float *state_prev, const float *Z,
-                      float *state_new, int n_atoms, float *node_scratch, cudaStream_t st);
 int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
                          const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st, int *wd = nullptr);
 int launch_state_update_tc(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,

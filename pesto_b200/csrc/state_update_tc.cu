@@ -1104,7 +1104,7 @@ int dispatch_tc(int nn, const void *tcw, int n_atoms, const int32_t *ids32, cons
 }  // namespace
 
 // Edge kernel only: attention sums of one layer -> Z[n_atoms+1][256] (row 0 unused).  nodeT / nodeC must hold the
-// layer's per-atom factors (launch_node_fused).
+// layer's per-atom factors (launch_node_umma).
 int launch_edge_tc_layer(const float *lw, const void *tcw, int nn, int n_atoms, const int32_t *ids32, const float *geom,
                          const float *state_in, float *node_scratch, float *Z, int mode, cudaStream_t st, int *wd) {
     if (!tcw) {
