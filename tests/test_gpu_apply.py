@@ -131,3 +131,36 @@ def test_structure_runner_equals_one_by_one(cuda_models, mode):
     assert [i for i, _ in got] == list(range(len(sizes)))
     for (i, z), ref in zip(got, singles):
         assert z.shape == ref.shape and (z - ref).abs().max().item() <= (2e-4 if mode == "fp32" else 3e-4), i
+
+
+def test_one_process_two_devices():
+    """One process, two GPUs: the dynamic shared-memory opt-in and the SM count of the persistent grids are per-device
+    attributes (csrc `device_setup`), the model keeps one packed handle and one workspace per device, the runner's staging
+    buffers are per device.  Skipped on a single-GPU box."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from conftest import load_config
+    from pesto_b200.data_encoding import extract_topology
+    from pesto_b200.model import Model
+    from pesto_b200.runner import predict_structures
+    from pesto_b200.synth import synth_structure, one_hot_features
+    sd = {k: torch.from_numpy(v) for k, v in load_weights("i_v4_0").items()}
+    model = Model.for_state_dict(load_config("i_v4_0"), sd, mode="f16x3").eval()
+    X, el, rid = synth_structure(700, 33)
+    q0, n_res = one_hot_features(el), int(rid.max()) + 1
+    zs = []
+    for d in (1, 0, 1):                                   # the second device first: nothing may be cached from device 0
+        dev = torch.device("cuda", d)
+        Xd = X.to(dev)
+        ids1 = extract_topology(Xd, 64)[0] + 1
+        z = model(Xd, ids1, q0.to(dev), rid.int().to(dev), n_res=n_res)
+        model.raise_if_failed(dev)
+        assert z.device == dev
+        zs.append(z.cpu())
+    assert torch.equal(zs[0], zs[2]) and (zs[0] - zs[1]).abs().max().item() < 1e-5
+    elems = np.asarray(["C", "N", "O", "S", "H"] * 6)
+    s = {"xyz": X.numpy(), "element": elems[np.minimum(el.numpy(), len(elems) - 1)], "resid": rid.numpy()}
+    out = [list(predict_structures(model, [s, s], device=f"cuda:{d}")) for d in (0, 1)]
+    assert all(len(o) == 2 for o in out) and (out[0][0][1] - out[1][0][1]).abs().max().item() < 1e-5
